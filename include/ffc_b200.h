@@ -1,0 +1,191 @@
+/*
+ * ffc_b200.h -- C ABI of libffc_b200.so: the B200-native FFC classification head.
+ *
+ * The reference (sqnkkang/Very-Large-Scale-Face-Recognition) has no FFI: its hot path is two
+ * Python classes, `LRU` (lru.py:21-255) and `FFC` (ffc.py:10-267).  This header is the boundary a
+ * maintainer binds with ctypes; every entry point names the reference code it
+ * replaces.  Conventions:
+ *   - plain C: pointers + sizes only, no C++/torch types; all `*_dev` pointers are CUDA device
+ *     pointers owned by the caller; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on error; ffc_last_error() gives the text.
+ *   - nothing synchronises the stream unless stated ("host-sync").  Not thread-safe per handle.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Slots, rows and labels are int32 on the device (the reference uses Python ints / int64 tensors;
+ * the Python mirror converts at the boundary).  Keys (identity labels) are int64; the two values
+ * INT64_MIN and INT64_MIN+1 are reserved as hash-table sentinels and are rejected.
+ */
+#ifndef FFC_B200_H_
+#define FFC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFC_OK 0
+#define FFC_ERR_INVALID 1
+#define FFC_ERR_CUDA 2
+#define FFC_ERR_STATE 3
+
+#define FFC_LOSS_AM 0  /* ffc.py:73-94  CosFace / additive margin */
+#define FFC_LOSS_ARC 1 /* ffc.py:95-115 ArcFace */
+#define FFC_LOSS_SV 2  /* ffc.py:116-138 SV-softmax variant (mask_svfc = 1.2, ffc.py:47) */
+
+#define FFC_PREC_BF16 0 /* tcgen05 bf16 tensor-core sweep (fp32 accumulate in TMEM)            */
+#define FFC_PREC_FP32 1 /* check mode: fp32 inputs, fp64 accumulate, SIMT, no tensor cores     */
+
+#define FFC_LRU_MAX_BATCH 1024 /* keys per ffc_lru_assign call (callers chunk larger batches) */
+#define FFC_TOPK_MAX 10        /* ffc.py:48 hard_neg <= 10 */
+
+const char* ffc_last_error(void);
+/* library / build info: returns e.g. "ffc_b200 0.1 sm_100a" */
+const char* ffc_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * LRU id -> slot cache on the device (replaces lru.py:21-255 and the bookkeeping loop
+ * ffc.py:162-177 / ffc.py:214-235).
+ * State: open-addressing hash table key->slot (32-cell windows probed by one warp), slot_key[],
+ * last_pos[] and a log-structured recency ring (one record per access; a record is live iff
+ * last_pos[slot] == its ring position), cur_idx, an undo journal.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ffc_lru ffc_lru_t;
+
+/* lru.py:27-40 LRU.__init__(capacity).  journal_capacity: max outstanding journaled accesses
+ * (try_get without rollback); 0 -> default 65536. */
+int ffc_lru_create(int64_t capacity, int64_t journal_capacity, ffc_lru_t** out);
+int ffc_lru_destroy(ffc_lru_t* h);
+/* lru.py:132-141 clear(); unlike the reference it also resets cur_idx (the reference's clear()
+ * leaves the object unusable). */
+int ffc_lru_clear(ffc_lru_t* h, void* stream);
+
+/* B sequential accesses, in order, with the FFC bookkeeping folded in:
+ *   journal == 0: lru.py:44-89  get()      for each key   (ffc.py:166-177)
+ *   journal != 0: lru.py:157-204 try_get() for each key   (ffc.py:219-235), undo with ffc_lru_undo
+ * Per position i:  cols_out[i] = slot;  rows_out[i] = 0 for a miss (and qpos[slot] = 1), or the
+ * slot's qpos for a hit (then qpos[slot] ^= 1)              (ffc.py:167-177);
+ * hit_out[i] = 1 for a hit.  Slots that were hit at least once are appended to ones_list_dev /
+ * *n_ones_dev (a set: each slot once) and their bit is set in cmask_dev (bit s of word s/32) --
+ * ffc.py:165,176 `ones_idx`.  qpos_dev (uint8[capacity]) is ffc.py:41-43 queue_position_dict; pass
+ * NULL for a plain LRU (rows_out is then 0 for misses and 1 for hits... unspecified; pass NULL too).
+ * Any of rows_out, hit_out, ones_list_dev, n_ones_dev, cmask_dev may be NULL.
+ * 1 <= n <= FFC_LRU_MAX_BATCH.  n_ones_dev is accumulated (caller zeroes it). */
+int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int journal, uint8_t* qpos_dev,
+                   int32_t* rows_out, int32_t* cols_out, uint8_t* hit_out, int32_t* ones_list_dev,
+                   int32_t* n_ones_dev, uint32_t* cmask_dev, void* stream);
+
+/* lru.py:147-151 view() / lru.py:145-146 __contains__ for n keys: slot or -1, recency untouched
+ * (ffc.py:189-194 / 242-246 probe labels).  Any n >= 1. */
+int ffc_lru_view(ffc_lru_t* h, const int64_t* keys_dev, int n, int32_t* slots_out, void* stream);
+
+/* lru.py:252-255 rollback_steps(steps): undo the newest `steps` journaled accesses (clamped to the
+ * journal length, like the reference) including their qpos changes (ffc.py:256-257). */
+int ffc_lru_undo(ffc_lru_t* h, int64_t steps, uint8_t* qpos_dev, void* stream);
+
+/* Bounded maintenance between passes (ring compaction, hash-table rebuild) when the host-side
+ * conservative counters say so; never changes observable state. */
+int ffc_lru_maintain(ffc_lru_t* h, void* stream);
+
+/* host-sync: number of resident keys (== cur_idx) and outstanding journal length */
+int ffc_lru_size(ffc_lru_t* h, int64_t* cur_idx_out, int64_t* journal_len_out, void* stream);
+/* host-sync: lru.py:102-108 state_dict(): (key, slot) pairs from most to least recently used, into
+ * HOST arrays of at least `capacity` entries; *n_out = count. */
+int ffc_lru_export(ffc_lru_t* h, int64_t* keys_host, int32_t* slots_host, int64_t* n_out, void* stream);
+/* host-sync: lru.py:113-128 restore(kvs): requires an empty cache (cur_idx == 0), n <= capacity,
+ * distinct keys and distinct slots in [0, capacity). pairs are most- to least-recent. */
+int ffc_lru_import(ffc_lru_t* h, const int64_t* keys_host, const int32_t* slots_host, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prototype queue scatter (replaces ffc.py:179-182, 237-241, 255).
+ * queue_f32_dev: [2, Q, D] fp32 (the reference's `queue` buffer, checkpoint contract 'fc').
+ * queue_bf16_dev: [2, Q, D] bf16 mirror read by the tensor-core sweep (may be NULL).
+ * For each i: queue[rows[i], cols[i], :] = g[i, :]; a repeated (row, col) pair resolves to the LAST
+ * occurrence (the reference's serial CPU behaviour; undefined on its CUDA path).
+ * undo_f32_dev ([B, D] fp32, may be NULL): receives the previous fp32 row of every winning write so
+ * that ffc_queue_restore can put it back (ffc.py:240 `old_tensor`, ffc.py:255).
+ * ---------------------------------------------------------------------------------------------- */
+int ffc_queue_scatter(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
+                      const int32_t* cols_dev, const float* g_dev, int B, int64_t Q, int D,
+                      float* undo_f32_dev, void* stream);
+int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
+                      const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
+                      void* stream);
+/* fp32 -> bf16 mirror of n contiguous elements (queue initialisation / checkpoint load). */
+int ffc_cast_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused margin-softmax head pass (replaces ffc.py:195-202 / 248-254, add_margin ffc.py:60-138 and
+ * its autograd backward): loss = add_margin(p . queue[0]^T, label) + add_margin(p . W2^T, label),
+ * W2 = queue[1] on the `ones` slots and queue[0] elsewhere, plus dLoss/dp -- without materialising
+ * the B x Q logits.  One sweep over the (local shard of the) queue accumulates, per probe row, the
+ * softmax denominator, sum_j softmax_j * W_j (the embedding gradient) and the running top-k of the
+ * hard-negative term; columns that differ between the two losses (`ones`) and each row's target
+ * column are excluded from the sweep and handled in two small side sweeps / gather-dots.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ffc_head ffc_head_t;
+
+typedef struct ffc_head_config {
+  int32_t max_rows;      /* max probe rows per pass (all ranks' rows when sharded) */
+  int64_t q_local;       /* queue rows (slots) held by this rank */
+  int64_t q_total;       /* global queue size (== q_local on one GPU) */
+  int64_t col_offset;    /* global slot index of local row 0 */
+  int32_t feat_dim;      /* D: multiple of 64, <= 512 for the bf16 path */
+  int32_t loss_type;     /* FFC_LOSS_* */
+  float scale;           /* ffc.py:34 */
+  float margin;          /* ffc.py:35 */
+  int32_t topk;          /* ffc.py:48 hard_neg, 1..FFC_TOPK_MAX */
+  int32_t precision;     /* FFC_PREC_* */
+} ffc_head_config;
+
+int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out);
+int ffc_head_destroy(ffc_head_t* h);
+
+/* Inputs of one pass; all device pointers. */
+typedef struct ffc_head_pass {
+  const float* p_f32;          /* [n_rows, D] probe embeddings (unit norm, ffc.py:157/209) */
+  const float* queue_f32;      /* [2, q_local, D] */
+  const void* queue_bf16;      /* [2, q_local, D] bf16 mirror (bf16 path) */
+  const int32_t* label;        /* [n_rows] global slot or -1 (ffc.py:194/246) */
+  const int32_t* ones_list;    /* [<= max_rows] GLOBAL slots hit in this pass's bookkeeping (ffc.py:197) */
+  const int32_t* n_ones;       /* device scalar */
+  const uint32_t* cmask;       /* bitmask over LOCAL slots: bit set <=> slot in ones_list; may be NULL iff n_ones==0 always */
+  int32_t n_rows;
+} ffc_head_pass;
+
+/* Rank-local statistics produced by the sweep, consumed by finalize.  Layout (all fp32 unless
+ * noted), n = n_rows, k = topk, D = feat_dim:
+ *   lsum   [3][n]      softmax denominators (relative to the fixed max m = c*scale): common, side0, side1
+ *   osum   [3][n][D]   sum_j p~_ij W_j for the same three column sets
+ *   tgt    [4][n]      cos_t under queue[0], cos_t under W2, (owner flag as 1.0/0.0), spare
+ *   topv   [3][n][k]   running top-k cosines (descending; -inf padded), topi int32 [3][n][k] GLOBAL slots
+ * On several GPUs the caller sums lsum/tgt across ranks (all-reduce), all-gathers topv/topi, then
+ * calls finalize, then reduce-scatters dp.  ffc_head_stats_bytes gives the sizes. */
+typedef struct ffc_head_stats {
+  float* lsum;
+  float* osum;
+  float* tgt;
+  float* topv;
+  int32_t* topi;
+} ffc_head_stats;
+
+int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream);
+
+/* Finalize: loss_out[0] += this pass's loss (both add_margin terms) -- identical on every rank when
+ * stats were reduced; dp_out [n_rows, D] fp32 = this rank's contribution to dLoss/dp (the whole
+ * gradient on one GPU).  n_ranks_topk: number of gathered top-k candidate sets in stats->topv/topi
+ * ([n_ranks][3][n][k]); 1 on one GPU.  n_pos/n_out (global counts of label!=-1 / ==-1 rows) are
+ * computed on the device from `label`. */
+int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats,
+                      int n_ranks_topk, float* loss_out, float* dp_out, void* stream);
+
+/* sizes in bytes of the five stats arrays for n rows (one rank's worth) */
+int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]);
+
+/* Debug / evidence: number of kernel launches issued by this library since load. */
+int64_t ffc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFC_B200_H_ */

@@ -1,0 +1,688 @@
+// Fused margin-softmax head: handle, prep, check-mode (fp32 in / fp64 accumulate, SIMT) sweep,
+// partial reduce and finalize.  Replaces ffc.py:195-202 / 248-254 + add_margin (ffc.py:60-138) and
+// its autograd backward.  The tcgen05 sweep lives in head_sm100.cu and produces the same partials.
+//
+// Math (per probe row i, loss l in {1,2}; s = scale, M = fixed max, f = margin function):
+//   p~_ij = exp(s*z_ij - M) over all columns j except the target t_i and the `ones` set C
+//   L_l   = sum_common p~ + sum_{j in C\{t}} p~(W_l[j]) + exp(s*f(cos_t,l) - M)
+//   CE_l  = log L_l + M - s*f(cos_t,l)                                  (F.cross_entropy, ffc.py:83/104/127)
+//   dCE_l/dp = s * [ (O_common + O_side,l)/L_l + (e_t/L_l - 1) * f'(cos_t,l) * W_l[t] ]
+// with W_1 = queue[0], W_2 = queue[1] on C and queue[0] elsewhere (ffc.py:197-200), O = sum p~_j W_j.
+// Hard negatives (ffc.py:86-92): mean over outlier rows and their top-k cosines of max(cos, 0).
+#include <algorithm>
+#include <math.h>
+
+#include "head_internal.cuh"
+
+struct ffc_head {
+  ffc_head_config cfg;
+  int64_t part_rows_cap;
+  int max_chunks;
+  // workspace
+  __nv_bfloat16* p16;
+  float* side_f32;             // [2][max_rows][D]
+  __nv_bfloat16* side_bf16;    // [2][max_rows][D]
+  int32_t* tcol;               // [max_rows]  target column in the main sweep (local) or -1
+  int32_t* tpos;               // [max_rows]  target position in ones_list or -1
+  uint8_t* is_out;             // [max_rows]
+  float* thr;                  // [2][max_rows]
+  int32_t* counts;             // [2] n_pos, n_out
+  float* row_loss;             // [max_rows]
+  float* l_part;
+  float* o_part;
+  float* topv_part;
+  int32_t* topi_part;
+  ffc::Sm100Cache* sm100;
+};
+
+namespace ffc {
+
+// ------------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) head_prep_rows_kernel(const int32_t* __restrict__ label, int n_rows, int64_t col_offset, int64_t q_local,
+                                                             const uint32_t* __restrict__ cmask, const int32_t* __restrict__ ones_list,
+                                                             const int32_t* __restrict__ n_ones_p, int32_t* __restrict__ tcol,
+                                                             int32_t* __restrict__ tpos, uint8_t* __restrict__ is_out, int32_t* counts) {
+  // one block per row so that the ones_list search is parallel
+  const int i = blockIdx.x;
+  const int32_t lab = label[i];
+  int32_t tc = -1;
+  if (lab >= 0) {
+    const int64_t loc = (int64_t)lab - col_offset;
+    if (loc >= 0 && loc < q_local) tc = (int32_t)loc;
+  }
+  __shared__ int found;
+  if (threadIdx.x == 0) found = -1;
+  __syncthreads();
+  const bool in_c = (tc >= 0) && cmask && ((cmask[tc >> 5] >> (tc & 31)) & 1u);
+  if (in_c) {
+    const int no = *n_ones_p;
+    for (int j = threadIdx.x; j < no; j += blockDim.x)
+      if (ones_list[j] == tc) found = j;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tcol[i] = tc;
+    tpos[i] = found;
+    is_out[i] = lab < 0;
+    atomicAdd(&counts[lab < 0 ? 1 : 0], 1);
+  }
+}
+
+// side matrices: W_side0[j] = queue[0][ones[j]], W_side1[j] = queue[1][ones[j]]
+__global__ void __launch_bounds__(128) head_gather_side_kernel(const float* __restrict__ qf, const __nv_bfloat16* __restrict__ qh, int64_t q_local, int D,
+                                                               const int32_t* __restrict__ ones_list, const int32_t* __restrict__ n_ones_p,
+                                                               int max_rows, float* __restrict__ side_f32, __nv_bfloat16* __restrict__ side_bf16) {
+  const int j = blockIdx.x;
+  const int no = *n_ones_p;
+  const bool live = j < no;
+  const int64_t slot = live ? ones_list[j] : 0;
+  for (int r = 0; r < 2; ++r) {
+    const int64_t src = ((int64_t)r * q_local + slot) * D;
+    const int64_t dst = ((int64_t)r * max_rows + j) * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      if (side_f32) side_f32[dst + d] = live ? qf[src + d] : 0.f;
+      if (side_bf16) side_bf16[dst + d] = live ? qh[src + d] : __float2bfloat16(0.f);
+    }
+  }
+}
+
+// target cosines: tgt[0] = p . queue[0][t], tgt[1] = p . (t in C ? queue[1][t] : queue[0][t]), tgt[2] = owner
+template <bool BF16>
+__global__ void __launch_bounds__(128) head_target_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__ P16, const float* __restrict__ qf,
+                                                          const __nv_bfloat16* __restrict__ qh, int64_t q_local, int D, int n_rows,
+                                                          const int32_t* __restrict__ tcol, const int32_t* __restrict__ tpos, float margin,
+                                                          float* __restrict__ tgt, float* __restrict__ thr) {
+  const int i = blockIdx.x;
+  const int32_t tc = tcol[i];
+  double a0 = 0.0, a1 = 0.0;
+  if (tc >= 0) {
+    const int64_t r0 = (int64_t)tc * D;
+    const int64_t r1 = (tpos[i] >= 0) ? ((int64_t)q_local + tc) * D : r0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float p, w0, w1;
+      if (BF16) {
+        p = __bfloat162float(P16[(int64_t)i * D + d]);
+        w0 = __bfloat162float(qh[r0 + d]);
+        w1 = __bfloat162float(qh[r1 + d]);
+      } else {
+        p = P[(int64_t)i * D + d];
+        w0 = qf[r0 + d];
+        w1 = qf[r1 + d];
+      }
+      a0 += (double)p * w0;
+      a1 += (double)p * w1;
+    }
+  }
+  __shared__ double s0[128], s1[128];
+  s0[threadIdx.x] = a0;
+  s1[threadIdx.x] = a1;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s0[threadIdx.x] += s0[threadIdx.x + o];
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float c0 = (float)s0[0], c1 = (float)s1[0];
+    tgt[0 * n_rows + i] = tc >= 0 ? c0 : 0.f;
+    tgt[1 * n_rows + i] = tc >= 0 ? c1 : 0.f;
+    tgt[2 * n_rows + i] = tc >= 0 ? 1.f : 0.f;
+    tgt[3 * n_rows + i] = 0.f;
+    if (thr) {
+      thr[i] = tc >= 0 ? c0 - margin : INFINITY;
+      thr[n_rows + i] = tc >= 0 ? c1 - margin : INFINITY;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// check-mode sweep: fp32 inputs, fp64 arithmetic, no tensor cores.  Block = 256 threads,
+// 16 probe rows x one column chunk, 32 columns per step.
+// ------------------------------------------------------------------------------------------------
+constexpr int SR = 16;   // rows per block
+constexpr int SC = 32;   // columns per step
+
+__global__ void __launch_bounds__(256) head_sweep_simt_kernel(const SweepArgs a, int64_t cols_per_chunk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = a.D;
+  float* sP = reinterpret_cast<float*>(smem_raw);                  // [SR][D]
+  float* sW = sP + SR * D;                                         // [SC][D]
+  double* sG = reinterpret_cast<double*>(sW + SC * D);             // [SR][SC]  cos, then g~
+  double* sL = sG + SR * SC;                                       // [SR]
+  float* sTv = reinterpret_cast<float*>(sL + SR);                  // [SR][KMAX]
+  int32_t* sTi = reinterpret_cast<int32_t*>(sTv + SR * KMAX);      // [SR][KMAX]
+
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * SR;
+  const int chunk = blockIdx.y;
+  const int64_t n_cols = a.n_cols_dev ? (int64_t)*a.n_cols_dev : a.n_cols;
+  const int64_t c_begin = (int64_t)chunk * cols_per_chunk;
+  int64_t c_end = c_begin + cols_per_chunk;
+  if (c_end > n_cols) c_end = n_cols;
+
+  for (int e = tid; e < SR * D; e += 256) {
+    const int r = e / D, d = e - r * D;
+    sP[e] = (row0 + r < a.n_rows) ? a.P_f32[(int64_t)(row0 + r) * D + d] : 0.f;
+  }
+  if (tid < SR) {
+    sL[tid] = 0.0;
+    for (int q = 0; q < KMAX; ++q) {
+      sTv[tid * KMAX + q] = -INFINITY;
+      sTi[tid * KMAX + q] = -1;
+    }
+  }
+  const int orow = tid >> 4, od0 = tid & 15;   // O accumulation mapping: row, d = od0 + 16*q
+  double acc[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) acc[q] = 0.0;
+  const double s = a.scale, M = a.fixed_max;
+  __syncthreads();
+
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += SC) {
+    const int nc = (int)((c_end - c0 < SC) ? (c_end - c0) : SC);
+    for (int e = tid; e < SC * D; e += 256) {
+      const int c = e / D, d = e - c * D;
+      sW[e] = (c < nc) ? a.W_f32[(c0 + c) * D + d] : 0.f;
+    }
+    __syncthreads();
+    // phase A: 16 x 32 cosines, two per thread
+    for (int e = tid; e < SR * SC; e += 256) {
+      const int r = e / SC, c = e - r * SC;
+      double dot = 0.0;
+      const float* pr = sP + r * D;
+      const float* wc = sW + c * D;
+      for (int d = 0; d < D; ++d) dot += (double)pr[d] * (double)wc[d];
+      sG[e] = dot;
+    }
+    __syncthreads();
+    // phase B: one thread per row: exclusions, exp, denominator, top-k
+    if (tid < SR) {
+      const int r = tid, gr = row0 + r;
+      if (gr < a.n_rows) {
+        const int32_t tc = a.tcol[gr];
+        const double th = a.thr ? (double)a.thr[gr] : (double)INFINITY;
+        const bool outl = a.is_out[gr];
+        float tv[KMAX];
+        int32_t ti[KMAX];
+        for (int q = 0; q < KMAX; ++q) {
+          tv[q] = sTv[r * KMAX + q];
+          ti[q] = sTi[r * KMAX + q];
+        }
+        double lsum = 0.0;
+        for (int c = 0; c < SC; ++c) {
+          const int64_t col = c0 + c;
+          bool excl = (c >= nc) || (col == tc);
+          if (!excl && a.cmask) excl = (a.cmask[col >> 5] >> (col & 31)) & 1u;
+          double g = 0.0;
+          if (!excl) {
+            const double cs = sG[r * SC + c];
+            double z = cs, coef = 1.0;
+            if (a.sv && cs > th) {
+              z = (double)SV_T * cs + (double)SV_T - 1.0;
+              coef = (double)SV_T;
+            }
+            const double pt = exp(s * z - M);
+            lsum += pt;
+            g = pt * coef;
+            if (outl && (float)cs > tv[a.k - 1]) topk_insert<KMAX>(tv, ti, a.k, (float)cs, (int32_t)col);
+          }
+          sG[r * SC + c] = g;
+        }
+        sL[r] += lsum;
+        for (int q = 0; q < KMAX; ++q) {
+          sTv[r * KMAX + q] = tv[q];
+          sTi[r * KMAX + q] = ti[q];
+        }
+      } else {
+        for (int c = 0; c < SC; ++c) sG[r * SC + c] = 0.0;
+      }
+    }
+    __syncthreads();
+    // phase C: O[r][d] += g~[r][c] * W[c][d]
+    for (int c = 0; c < nc; ++c) {
+      const double g = sG[orow * SC + c];
+      if (g != 0.0) {
+        const float* wc = sW + c * D;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int d = od0 + 16 * q;
+          if (d < D) acc[q] += g * (double)wc[d];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // write partials
+  const int gr = row0 + orow;
+  if (gr < a.n_rows) {
+    float* op = a.o_part + ((int64_t)chunk * a.n_rows + gr) * D;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int d = od0 + 16 * q;
+      if (d < D) op[d] = (float)acc[q];
+    }
+  }
+  if (tid < SR && row0 + tid < a.n_rows) {
+    const int64_t pr = (int64_t)chunk * a.n_rows + row0 + tid;
+    a.l_part[pr] = (float)sL[tid];
+    for (int q = 0; q < a.k; ++q) {
+      a.topv_part[pr * a.k + q] = sTv[tid * KMAX + q];
+      a.topi_part[pr * a.k + q] = sTi[tid * KMAX + q];
+    }
+  }
+}
+
+int launch_sweep_simt(const SweepArgs& a, cudaStream_t s) {
+  FFC_REQUIRE(a.D <= 512, "check-mode sweep: D=%d > 512", a.D);
+  const int row_tiles = (a.n_rows + SR - 1) / SR;
+  const int64_t cpc = ((ceil_div64(a.n_cols, a.n_chunks) + SC - 1) / SC) * SC;
+  const size_t smem = (size_t)(SR + SC) * a.D * sizeof(float) + (SR * SC + SR) * sizeof(double) + SR * KMAX * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FFC_CUDA(cudaFuncSetAttribute(head_sweep_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(row_tiles, a.n_chunks);
+  head_sweep_simt_kernel<<<grid, 256, smem, s>>>(a, cpc);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+static int simt_pick_chunks(int n_rows, int64_t n_cols) {
+  const int row_tiles = (n_rows + SR - 1) / SR;
+  int64_t c = (4 * 148) / std::max(row_tiles, 1);
+  c = std::min<int64_t>(c, ceil_div64(n_cols, SC));
+  return (int)std::max<int64_t>(c, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce partials over chunks -> stats slot `slot` (lsum/osum) and top-k slot `tslot` (or -1)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) head_reduce_kernel(const float* __restrict__ l_part, const float* __restrict__ o_part,
+                                                          const float* __restrict__ topv_part, const int32_t* __restrict__ topi_part, int n_chunks,
+                                                          int n_rows, int D, int k, float* __restrict__ lsum, float* __restrict__ osum,
+                                                          float* __restrict__ topv, int32_t* __restrict__ topi, const uint8_t* __restrict__ is_out,
+                                                          int64_t idx_base, const int32_t* __restrict__ idx_map) {
+  const int i = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < n_chunks; ++c) acc += o_part[((int64_t)c * n_rows + i) * D + d];
+    osum[(int64_t)i * D + d] = acc;
+  }
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int c = 0; c < n_chunks; ++c) acc += l_part[(int64_t)c * n_rows + i];
+    lsum[i] = acc;
+    if (topv) {
+      float tv[KMAX];
+      int32_t ti[KMAX];
+      for (int q = 0; q < KMAX; ++q) {
+        tv[q] = -INFINITY;
+        ti[q] = -1;
+      }
+      if (is_out[i]) {
+        for (int c = 0; c < n_chunks; ++c)
+          for (int q = 0; q < k; ++q) {
+            const float v = topv_part[((int64_t)c * n_rows + i) * k + q];
+            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, topi_part[((int64_t)c * n_rows + i) * k + q]);
+          }
+      }
+      for (int q = 0; q < k; ++q) {
+        topv[(int64_t)i * k + q] = tv[q];
+        int32_t id = ti[q];
+        if (id >= 0) id = (int32_t)(idx_base + (idx_map ? idx_map[id] : id));   // -> global slot
+        topi[(int64_t)i * k + q] = id;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize
+// ------------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  const float* P;              // [n][D]  (fp32 embeddings; only for nothing but kept for symmetry)
+  const float* qf;             // [2][q_local][D]
+  const __nv_bfloat16* qh;
+  int use_bf16_rows;           // gather W rows from the bf16 mirror (consistent with the tensor-core sweep)
+  const int32_t* label;
+  const int32_t* tcol;
+  const int32_t* tpos;
+  const uint8_t* is_out;
+  const int32_t* counts;
+  const float* lsum;           // [4][n]
+  const float* osum;           // [4][n][D]
+  const float* tgt;            // [4][n]
+  const float* topv;           // [n_ranks][3][n][k]
+  const int32_t* topi;
+  int n_ranks;
+  int n, D, k;
+  int64_t q_local, col_offset;
+  int loss_type;
+  float scale, margin, fixed_max;
+  float* row_loss;
+  float* dp;
+};
+
+__device__ __forceinline__ float w_elem(const FinalizeArgs& a, int r, int64_t local_slot, int d) {
+  const int64_t off = ((int64_t)r * a.q_local + local_slot) * a.D + d;
+  return a.use_bf16_rows ? __bfloat162float(a.qh[off]) : a.qf[off];
+}
+
+__global__ void __launch_bounds__(128) head_finalize_kernel(const FinalizeArgs a) {
+  const int i = blockIdx.x, n = a.n, D = a.D, k = a.k;
+  const int n_pos = a.counts[0], n_out = a.counts[1];
+  __shared__ float sh_coefO[2], sh_coefT[2];
+  __shared__ float sh_w[2 * KMAX];
+  __shared__ int32_t sh_slot[2 * KMAX];
+  __shared__ int sh_row[2 * KMAX];
+  __shared__ int sh_nw;
+  const bool outl = a.is_out[i];
+  if (threadIdx.x == 0) {
+    float loss = 0.f;
+    sh_nw = 0;
+    if (!outl) {
+      const double s = a.scale, M = a.fixed_max, m = a.margin;
+      for (int l = 0; l < 2; ++l) {
+        const double ct = a.tgt[l * n + i];
+        double ft, dft;
+        if (a.loss_type == FFC_LOSS_AM) {
+          ft = ct - m;
+          dft = 1.0;
+        } else if (a.loss_type == FFC_LOSS_ARC) {
+          const double sn = sqrt(1.0 - ct * ct);      // NaN for |ct| > 1, like ffc.py:101
+          ft = ct * cos(m) - sn * sin(m);
+          dft = cos(m) + ct * sin(m) / sn;
+        } else {
+          ft = ct > m ? ct - m : ct;
+          dft = 1.0;
+        }
+        const double zt = s * ft;
+        const double et = exp(zt - M);
+        const double L = (double)a.lsum[l * n + i] + (double)a.lsum[(2 + l) * n + i] + et;
+        loss += (float)((log(L) + M - zt) / (double)n_pos);
+        sh_coefO[l] = (float)(s / L / (double)n_pos);
+        sh_coefT[l] = (float)(s * (et / L - 1.0) * dft / (double)n_pos);
+      }
+    } else {
+      // merge top-k candidates per loss: common (all ranks) + side_l (all ranks)
+      const float wneg = 1.f / ((float)n_out * (float)k);
+      for (int l = 0; l < 2; ++l) {
+        float tv[KMAX];
+        int32_t ti[KMAX];
+        for (int q = 0; q < KMAX; ++q) {
+          tv[q] = -INFINITY;
+          ti[q] = -1;
+        }
+        for (int r = 0; r < a.n_ranks; ++r)
+          for (int src = 0; src < 2; ++src) {
+            const int set = src == 0 ? 0 : 1 + l;
+            const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
+            for (int q = 0; q < k; ++q) {
+              const float v = a.topv[base + q];
+              // encode the source in the sign-free upper bit of a side index: side entries use W_l rows
+              if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, (int32_t)(a.topi[base + q] | (src ? 0x40000000 : 0)));
+            }
+          }
+        for (int q = 0; q < k; ++q) {
+          if (ti[q] < 0) continue;
+          const float v = tv[q];
+          loss += (v > 0.f ? v : 0.f) * wneg;
+          if (v >= 0.f) {
+            const int e = sh_nw++;
+            sh_w[e] = wneg;
+            sh_slot[e] = ti[q] & 0x3fffffff;
+            sh_row[e] = (ti[q] & 0x40000000) ? l : 0;   // side entry under loss 2 reads queue[1]
+          }
+        }
+      }
+    }
+    a.row_loss[i] = loss;
+  }
+  __syncthreads();
+  const int32_t tc = a.tcol[i];
+  const int trow2 = (a.tpos[i] >= 0) ? 1 : 0;
+  const int nw = sh_nw;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float g = 0.f;
+    if (!outl) {
+      g = sh_coefO[0] * (a.osum[((int64_t)0 * n + i) * D + d] + a.osum[((int64_t)2 * n + i) * D + d]) +
+          sh_coefO[1] * (a.osum[((int64_t)1 * n + i) * D + d] + a.osum[((int64_t)3 * n + i) * D + d]);
+      if (tc >= 0) g += sh_coefT[0] * w_elem(a, 0, tc, d) + sh_coefT[1] * w_elem(a, trow2, tc, d);
+    } else {
+      for (int e = 0; e < nw; ++e) {
+        const int64_t loc = (int64_t)sh_slot[e] - a.col_offset;
+        if (loc >= 0 && loc < a.q_local) g += sh_w[e] * w_elem(a, sh_row[e], loc, d);
+      }
+    }
+    a.dp[(int64_t)i * D + d] = g;
+  }
+}
+
+__global__ void __launch_bounds__(1024) head_loss_sum_kernel(const float* __restrict__ row_loss, int n, float* loss_out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += row_loss[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] += (float)sh[0];
+}
+
+__global__ void head_p_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
+}
+
+static float fixed_max_of(const ffc_head_config& c) { return c.loss_type == FFC_LOSS_SV ? c.scale * (2.f * SV_T - 1.f) : c.scale; }
+
+}  // namespace ffc
+
+using namespace ffc;
+
+extern "C" int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]) {
+  FFC_REQUIRE(cfg && sizes_out && n_rows >= 0, "ffc_head_stats_bytes: bad arguments");
+  const int64_t n = n_rows, D = cfg->feat_dim, k = cfg->topk;
+  sizes_out[0] = 4 * n * sizeof(float);
+  sizes_out[1] = 4 * n * D * sizeof(float);
+  sizes_out[2] = 4 * n * sizeof(float);
+  sizes_out[3] = 3 * n * k * sizeof(float);
+  sizes_out[4] = 3 * n * k * sizeof(int32_t);
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
+  FFC_REQUIRE(cfg && out, "ffc_head_create: NULL argument");
+  FFC_REQUIRE(cfg->max_rows >= 1 && cfg->q_local >= 1 && cfg->q_total >= cfg->q_local && cfg->col_offset >= 0, "ffc_head_create: bad sizes");
+  FFC_REQUIRE(cfg->q_total < 0x40000000, "ffc_head_create: queue size must be below 2^30");
+  FFC_REQUIRE(cfg->feat_dim >= 4 && cfg->feat_dim % 4 == 0 && cfg->feat_dim <= 512, "ffc_head_create: feat_dim %d (multiple of 4, <= 512)", cfg->feat_dim);
+  FFC_REQUIRE(cfg->loss_type >= 0 && cfg->loss_type <= 2, "ffc_head_create: loss_type %d", cfg->loss_type);
+  FFC_REQUIRE(cfg->topk >= 1 && cfg->topk <= KMAX, "ffc_head_create: topk %d outside [1,%d]", cfg->topk, KMAX);
+  FFC_REQUIRE(cfg->precision == FFC_PREC_BF16 || cfg->precision == FFC_PREC_FP32, "ffc_head_create: precision %d", cfg->precision);
+  if (cfg->precision == FFC_PREC_BF16) {
+    FFC_REQUIRE(cfg->feat_dim % 64 == 0, "ffc_head_create: the bf16 tensor-core path needs feat_dim %% 64 == 0 (got %d)", cfg->feat_dim);
+    // exp(s*z - M) must stay a normal float: range 2*M
+    FFC_REQUIRE(cfg->scale + fixed_max_of(*cfg) < 87.f, "ffc_head_create: scale %.1f too large for the fixed-max softmax (scale + M must be < 87)", cfg->scale);
+  }
+  ffc_head* h = new ffc_head();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  const int64_t R = cfg->max_rows, D = cfg->feat_dim;
+  h->part_rows_cap = std::max<int64_t>(R, 40960);
+  h->max_chunks = 1024;
+  FFC_CUDA(cudaMalloc(&h->p16, R * D * sizeof(__nv_bfloat16)));
+  FFC_CUDA(cudaMalloc(&h->side_f32, 2 * R * D * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->side_bf16, 2 * R * D * sizeof(__nv_bfloat16)));
+  FFC_CUDA(cudaMalloc(&h->tcol, R * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->tpos, R * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->is_out, R));
+  FFC_CUDA(cudaMalloc(&h->thr, 2 * R * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->counts, 2 * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->row_loss, R * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->l_part, h->part_rows_cap * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->o_part, h->part_rows_cap * D * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->topv_part, h->part_rows_cap * KMAX * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->topi_part, h->part_rows_cap * KMAX * sizeof(int32_t)));
+  if (cfg->precision == FFC_PREC_BF16) h->sm100 = sm100_cache_create();
+  *out = h;
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_destroy(ffc_head_t* h) {
+  if (!h) return FFC_OK;
+  cudaFree(h->p16);
+  cudaFree(h->side_f32);
+  cudaFree(h->side_bf16);
+  cudaFree(h->tcol);
+  cudaFree(h->tpos);
+  cudaFree(h->is_out);
+  cudaFree(h->thr);
+  cudaFree(h->counts);
+  cudaFree(h->row_loss);
+  cudaFree(h->l_part);
+  cudaFree(h->o_part);
+  cudaFree(h->topv_part);
+  cudaFree(h->topi_part);
+  if (h->sm100) sm100_cache_destroy(h->sm100);
+  delete h;
+  return FFC_OK;
+}
+
+static int run_one_sweep(ffc_head* h, SweepArgs a, int cache_slot, int stat_slot, int top_slot, const ffc_head_stats* out, int64_t idx_base,
+                         const int32_t* idx_map, cudaStream_t s) {
+  const bool bf16 = h->cfg.precision == FFC_PREC_BF16;
+  a.n_chunks = bf16 ? sm100_pick_chunks(a.n_rows, a.n_cols, a.D) : simt_pick_chunks(a.n_rows, a.n_cols);
+  FFC_REQUIRE((int64_t)a.n_chunks * a.n_rows <= h->part_rows_cap && a.n_chunks <= h->max_chunks, "head sweep: partial workspace too small (%d chunks x %d rows)",
+              a.n_chunks, a.n_rows);
+  a.l_part = h->l_part;
+  a.o_part = h->o_part;
+  a.topv_part = h->topv_part;
+  a.topi_part = h->topi_part;
+  int rc = bf16 ? launch_sweep_sm100(h->sm100, cache_slot, a, s) : launch_sweep_simt(a, s);
+  if (rc) return rc;
+  const int n = a.n_rows, D = a.D, k = a.k;
+  head_reduce_kernel<<<n, 128, 0, s>>>(a.l_part, a.o_part, a.topv_part, a.topi_part, a.n_chunks, n, D, k, out->lsum + (int64_t)stat_slot * n,
+                                       out->osum + (int64_t)stat_slot * n * D, top_slot >= 0 ? out->topv + (int64_t)top_slot * n * k : nullptr,
+                                       top_slot >= 0 ? out->topi + (int64_t)top_slot * n * k : nullptr, a.is_out, idx_base, idx_map);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
+  FFC_REQUIRE(h && in && out, "ffc_head_sweep: NULL argument");
+  const ffc_head_config& c = h->cfg;
+  const int n = in->n_rows, D = c.feat_dim;
+  FFC_REQUIRE(n >= 1 && n <= c.max_rows, "ffc_head_sweep: n_rows=%d outside [1,%d]", n, c.max_rows);
+  FFC_REQUIRE(in->p_f32 && in->queue_f32 && in->label && in->n_ones && in->ones_list, "ffc_head_sweep: NULL input");
+  FFC_REQUIRE(out->lsum && out->osum && out->tgt && out->topv && out->topi, "ffc_head_sweep: NULL stats");
+  const bool bf16 = c.precision == FFC_PREC_BF16;
+  FFC_REQUIRE(!bf16 || in->queue_bf16, "ffc_head_sweep: the bf16 path needs the bf16 queue mirror");
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* qf = in->queue_f32;
+  const __nv_bfloat16* qh = (const __nv_bfloat16*)in->queue_bf16;
+
+  FFC_CUDA(cudaMemsetAsync(h->counts, 0, 2 * sizeof(int32_t), s));
+  head_prep_rows_kernel<<<n, 128, 0, s>>>(in->label, n, c.col_offset, c.q_local, in->cmask, in->ones_list, in->n_ones, h->tcol, h->tpos, h->is_out,
+                                          h->counts);
+  FFC_LAUNCH_CHECK();
+  head_gather_side_kernel<<<c.max_rows, 128, 0, s>>>(qf, qh, c.q_local, D, in->ones_list, in->n_ones, c.max_rows, bf16 ? nullptr : h->side_f32,
+                                                     bf16 ? h->side_bf16 : nullptr);
+  FFC_LAUNCH_CHECK();
+  if (bf16) {
+    head_p_to_bf16_kernel<<<(int)std::min<int64_t>(ceil_div64((int64_t)n * D, 256), 1184), 256, 0, s>>>(in->p_f32, h->p16, (int64_t)n * D);
+    FFC_LAUNCH_CHECK();
+  }
+  const bool sv = c.loss_type == FFC_LOSS_SV;
+  if (bf16)
+    head_target_kernel<true><<<n, 128, 0, s>>>(in->p_f32, h->p16, qf, qh, c.q_local, D, n, h->tcol, h->tpos, c.margin, out->tgt, sv ? h->thr : nullptr);
+  else
+    head_target_kernel<false><<<n, 128, 0, s>>>(in->p_f32, h->p16, qf, qh, c.q_local, D, n, h->tcol, h->tpos, c.margin, out->tgt, sv ? h->thr : nullptr);
+  FFC_LAUNCH_CHECK();
+
+  SweepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P_f32 = in->p_f32;
+  a.P_bf16 = h->p16;
+  a.n_rows = n;
+  a.D = D;
+  a.is_out = h->is_out;
+  a.scale = c.scale;
+  a.fixed_max = fixed_max_of(c);
+  a.sv = sv;
+  a.k = c.topk;
+  int rc;
+  // main sweep(s) over queue[0]: everything except the target column and the `ones` columns
+  a.W_f32 = qf;
+  a.W_bf16 = qh;
+  a.n_cols = c.q_local;
+  a.n_cols_dev = nullptr;
+  a.tcol = h->tcol;
+  a.cmask = in->cmask;
+  a.thr = sv ? h->thr : nullptr;
+  if ((rc = run_one_sweep(h, a, 0, 0, 0, out, c.col_offset, nullptr, s))) return rc;
+  if (sv) {   // the SV hard-example threshold follows each loss's own target cosine (ffc.py:122)
+    a.thr = h->thr + n;
+    if ((rc = run_one_sweep(h, a, 0, 1, -1, out, c.col_offset, nullptr, s))) return rc;
+  } else {
+    FFC_CUDA(cudaMemcpyAsync(out->lsum + n, out->lsum, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    FFC_CUDA(cudaMemcpyAsync(out->osum + (int64_t)n * D, out->osum, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  // side sweeps over the gathered `ones` rows of queue[0] and queue[1]
+  a.n_cols = c.max_rows;
+  a.n_cols_dev = in->n_ones;
+  a.tcol = h->tpos;
+  a.cmask = nullptr;
+  for (int l = 0; l < 2; ++l) {
+    a.W_f32 = h->side_f32 + (int64_t)l * c.max_rows * D;
+    a.W_bf16 = h->side_bf16 + (int64_t)l * c.max_rows * D;
+    a.thr = sv ? h->thr + (int64_t)l * n : nullptr;
+    if ((rc = run_one_sweep(h, a, 1 + l, 2 + l, 1 + l, out, c.col_offset, in->ones_list, s))) return rc;
+  }
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out,
+                                 float* dp_out, void* stream) {
+  FFC_REQUIRE(h && in && stats && loss_out && dp_out, "ffc_head_finalize: NULL argument");
+  FFC_REQUIRE(n_ranks_topk >= 1, "ffc_head_finalize: n_ranks_topk must be >= 1");
+  const ffc_head_config& c = h->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  FinalizeArgs a;
+  a.P = in->p_f32;
+  a.qf = in->queue_f32;
+  a.qh = (const __nv_bfloat16*)in->queue_bf16;
+  a.use_bf16_rows = c.precision == FFC_PREC_BF16;
+  a.label = in->label;
+  a.tcol = h->tcol;
+  a.tpos = h->tpos;
+  a.is_out = h->is_out;
+  a.counts = h->counts;
+  a.lsum = stats->lsum;
+  a.osum = stats->osum;
+  a.tgt = stats->tgt;
+  a.topv = stats->topv;
+  a.topi = stats->topi;
+  a.n_ranks = n_ranks_topk;
+  a.n = in->n_rows;
+  a.D = c.feat_dim;
+  a.k = c.topk;
+  a.q_local = c.q_local;
+  a.col_offset = c.col_offset;
+  a.loss_type = c.loss_type;
+  a.scale = c.scale;
+  a.margin = c.margin;
+  a.fixed_max = fixed_max_of(c);
+  a.row_loss = h->row_loss;
+  a.dp = dp_out;
+  head_finalize_kernel<<<a.n, 128, 0, s>>>(a);
+  FFC_LAUNCH_CHECK();
+  head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}

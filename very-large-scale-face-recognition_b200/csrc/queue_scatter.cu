@@ -1,0 +1,110 @@
+// Prototype-queue enqueue / rollback scatter (replaces ffc.py:179-182, 237-241, 255).
+// One CTA per batch position: the CTA first scans the later positions for the same (row, col) pair
+// -- "last occurrence wins", the reference's serial index_put behaviour -- and only a winner moves
+// data: (optionally) save the old fp32 row, write the fp32 row with 16-byte stores and the bf16 mirror
+// row next to it.  B*D*(4+4+2) bytes per pass: latency-bound by construction.
+#include <algorithm>
+
+#include "ffc_common.cuh"
+
+namespace ffc {
+
+__device__ __forceinline__ bool later_duplicate(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int i, int B) {
+  const int32_t r = rows[i], c = cols[i];
+  bool dup = false;
+  for (int j = i + 1 + threadIdx.x; j < B; j += blockDim.x) dup |= (cols[j] == c && rows[j] == r);
+  return __syncthreads_or(dup);
+}
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+__global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ qf, __nv_bfloat16* __restrict__ qh, const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ cols, const float* __restrict__ g, int B, int64_t Q, int D,
+                                                            float* __restrict__ undo) {
+  const int i = blockIdx.x;
+  if (later_duplicate(rows, cols, i, B)) return;
+  const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
+  const float4* src = reinterpret_cast<const float4*>(g + (int64_t)i * D);
+  float4* dst = reinterpret_cast<float4*>(qf + off);
+  float4* und = undo ? reinterpret_cast<float4*>(undo + (int64_t)i * D) : nullptr;
+  for (int v = threadIdx.x; v < D / 4; v += blockDim.x) {
+    if (und) und[v] = dst[v];
+    const float4 x = src[v];
+    dst[v] = x;
+    if (qh) store_bf16x4(qh + off + 4 * v, x);
+  }
+}
+
+__global__ void __launch_bounds__(128) queue_restore_kernel(float* __restrict__ qf, __nv_bfloat16* __restrict__ qh, const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ cols, const float* __restrict__ undo, int B, int64_t Q, int D) {
+  const int i = blockIdx.x;
+  if (later_duplicate(rows, cols, i, B)) return;
+  const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
+  const float4* src = reinterpret_cast<const float4*>(undo + (int64_t)i * D);
+  float4* dst = reinterpret_cast<float4*>(qf + off);
+  for (int v = threadIdx.x; v < D / 4; v += blockDim.x) {
+    const float4 x = src[v];
+    dst[v] = x;
+    if (qh) store_bf16x4(qh + off + 4 * v, x);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    dst[i] = u;
+  }
+}
+
+}  // namespace ffc
+
+using namespace ffc;
+
+static int check_scatter_args(const void* qf, const void* rows, const void* cols, int B, int64_t Q, int D) {
+  FFC_REQUIRE(qf && rows && cols, "queue scatter: NULL argument");
+  FFC_REQUIRE(B >= 0 && Q >= 1 && D >= 4 && D % 4 == 0, "queue scatter: bad shape B=%d Q=%lld D=%d (D must be a multiple of 4)", B, (long long)Q, D);
+  return FFC_OK;
+}
+
+extern "C" int ffc_queue_scatter(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev, const int32_t* cols_dev, const float* g_dev,
+                                 int B, int64_t Q, int D, float* undo_f32_dev, void* stream) {
+  int rc = check_scatter_args(queue_f32_dev, rows_dev, cols_dev, B, Q, D);
+  if (rc) return rc;
+  FFC_REQUIRE(g_dev != nullptr, "ffc_queue_scatter: g is NULL");
+  if (B == 0) return FFC_OK;
+  queue_scatter_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, g_dev, B, Q, D,
+                                                             undo_f32_dev);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev, const int32_t* cols_dev,
+                                 const float* undo_f32_dev, int B, int64_t Q, int D, void* stream) {
+  int rc = check_scatter_args(queue_f32_dev, rows_dev, cols_dev, B, Q, D);
+  if (rc) return rc;
+  FFC_REQUIRE(undo_f32_dev != nullptr, "ffc_queue_restore: undo buffer is NULL");
+  if (B == 0) return FFC_OK;
+  queue_restore_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, undo_f32_dev, B, Q, D);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_cast_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n, void* stream) {
+  FFC_REQUIRE(src_dev && dst_bf16_dev && n >= 0 && n % 4 == 0, "ffc_cast_bf16: bad arguments (n must be a multiple of 4)");
+  if (n == 0) return FFC_OK;
+  const int64_t n4 = n / 4;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(n4, 256), 148 * 16);
+  cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src_dev, (uint2*)dst_bf16_dev, n4);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}

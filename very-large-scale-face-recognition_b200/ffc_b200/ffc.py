@@ -1,0 +1,283 @@
+"""Drop-in for the reference ``ffc.FFC`` (ffc.py:10-267) with the head on hand-written sm_100a kernels.
+
+``FFC(net_type, feat_dim, queue_size, scale, loss_type, margin, momentum, ...)`` and
+``FFC.forward(x, y, x_label, y_label) -> loss`` keep the reference's contract (main.py:64-65,116-117); the
+attributes callers read (``probe_net``, ``gallery_net``, ``queue``, ``lru``, ``queue_position_dict``, ``mask``)
+are there.  The head-level entry named by the build spec is :meth:`FFCHead.head`:
+``head(p, g, probe_label, gallery_label, commit) -> loss`` differentiable w.r.t. ``p``.
+
+Everything below the Python surface goes through the C ABI in include/ffc_b200.h; there is no PyTorch or CPU
+fallback for the head (a missing library or device raises).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+from torch.nn import Module
+
+from . import _capi
+from ._capi import HeadConfig, HeadPass, HeadStats, check, ptr
+from .lru import LRU
+
+
+def hard_neg_k(queue_size: int) -> int:
+    """ffc.py:48"""
+    return min(max(int(queue_size * 0.0002), 3), 10)
+
+
+class NormalizeNet(Module):
+    """Head-only stand-in backbone (``net_type='identity'``): L2-normalise the input embeddings, which is what
+    every reference backbone ends with (mobilefacenet_def.py:114, resnet_arcface.py:151, resnet_std.py:202)."""
+
+    def __init__(self, feat_dim=None, **_):
+        super().__init__()
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        return F.normalize(x + 0.0 * self.dummy)
+
+
+def _default_create_net(net_type, **kwargs):
+    if net_type in ('identity', 'none', None):
+        return NormalizeNet(**kwargs)
+    try:  # inside the reference tree this resolves to model/__init__.py:create_net
+        from model import create_net as ref_create_net
+    except ImportError as e:
+        raise ValueError(f"net_type {net_type!r}: backbones are outside this package; run inside the reference tree "
+                         "(its model/ package on sys.path), pass nn.Module instances via probe_net=/gallery_net=, "
+                         "or use net_type='identity' for head-only use") from e
+    return ref_create_net(net_type, **kwargs)
+
+
+create_net = _default_create_net
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, head, g, probe_label, gallery_label, commit):
+        loss, dp = head._pass(p.detach(), g, probe_label, gallery_label, commit)
+        ctx.save_for_backward(dp)
+        ctx.p_dtype = p.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dp,) = ctx.saved_tensors
+        return (dp * grad_out).to(ctx.p_dtype), None, None, None, None, None
+
+
+class FFCHead(Module):
+    """State and kernels of the FFC head: prototype queue [2,Q,D] (+ bf16 mirror), device LRU, queue positions."""
+
+    def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024):
+        super().__init__()
+        assert loss_type in ('AM', 'Arc', 'SV')
+        assert precision in _capi.PRECISIONS
+        self.feat_dim, self.queue_size = int(feat_dim), int(queue_size)
+        self.scale, self.margin, self.loss_type = float(scale), float(margin), loss_type
+        self.precision = precision
+        self.hard_neg = hard_neg_k(self.queue_size)
+        self.max_batch = int(max_batch)
+        self.register_buffer('queue', F.normalize(torch.rand(2, self.queue_size, self.feat_dim), dim=2))   # ffc.py:29-30
+        self.register_buffer('mask', torch.zeros(self.queue_size, 1))                                       # ffc.py:45
+        self._dev = None
+        self._lru = None
+        self._compact = {}
+        self._pending_lru = None
+        self._pending_qpos = None
+
+    # -- lazy device state ------------------------------------------------------------------------
+    def _ensure(self):
+        q = self.queue
+        if not q.is_cuda:
+            raise _capi.FFCError('the FFC head runs on a CUDA device only: move the module with .cuda() (no CPU fallback)')
+        if self._dev == q.device and self._lru is not None:
+            return
+        dev = q.device
+        self._lib = _capi.lib()
+        Q, D, R = self.queue_size, self.feat_dim, self.max_batch
+        with torch.cuda.device(dev):
+            self._lru = LRU(Q, device=dev)
+            self.qpos = torch.zeros(Q, dtype=torch.uint8, device=dev)
+            self.queue_bf16 = torch.empty(2, Q, D, dtype=torch.bfloat16, device=dev)
+            self.cmask = torch.zeros((Q + 31) // 32 + 1, dtype=torch.int32, device=dev)
+            self._alloc_batch(R)
+            cfg = HeadConfig(R, Q, Q, 0, D, _capi.LOSS_TYPES[self.loss_type], self.scale, self.margin, self.hard_neg,
+                             _capi.PRECISIONS[self.precision])
+            h = C.c_void_p()
+            check(self._lib.ffc_head_create(C.byref(cfg), C.byref(h)))
+            self._h, self._cfg = h, cfg
+        self._dev = dev
+        self.sync_mirror()
+        if self._pending_lru is not None:
+            self._lru.restore(self._pending_lru)
+            self._pending_lru = None
+        if self._pending_qpos is not None:
+            self.qpos.copy_(self._pending_qpos.to(dev))
+            self._pending_qpos = None
+
+    def _alloc_batch(self, R):
+        dev, D, k = self.queue.device, self.feat_dim, self.hard_neg
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.rows = torch.empty(R, **i32)
+        self.cols = torch.empty(R, **i32)
+        self.label = torch.empty(R, **i32)
+        self.ones_list = torch.empty(R, **i32)
+        self.n_ones = torch.zeros(1, **i32)
+        self.undo_rows = torch.empty(R, D, **f32)
+        self.loss_buf = torch.zeros(1, **f32)
+        self.stats = dict(lsum=torch.empty(4, R, **f32), osum=torch.empty(4, R, D, **f32), tgt=torch.empty(4, R, **f32),
+                          topv=torch.empty(3, R, k, **f32), topi=torch.empty(3, R, k, **i32))
+
+    def __del__(self):
+        h = self.__dict__.pop('_h', None)
+        if h:
+            try:
+                self._lib.ffc_head_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def lru(self):
+        """The device LRU (reference attribute ``ffc_net.lru``, main.py:85); created on first use."""
+        self._ensure()
+        return self._lru
+
+    def sync_mirror(self):
+        """Refresh the bf16 mirror from the fp32 queue (after construction / checkpoint load)."""
+        q = self.queue
+        assert q.is_contiguous() and q.dtype == torch.float32
+        check(self._lib.ffc_cast_bf16(q.data_ptr(), self.queue_bf16.data_ptr(), q.numel(), torch.cuda.current_stream(q.device).cuda_stream))
+
+    # -- reference attribute: ffc.py:41-43 ------------------------------------------------------------
+    @property
+    def queue_position_dict(self):
+        if self._lru is None:
+            src = self._pending_qpos if self._pending_qpos is not None else torch.zeros(self.queue_size, dtype=torch.uint8)
+        else:
+            src = self.qpos
+        return dict(enumerate(src.cpu().tolist()))
+
+    @queue_position_dict.setter
+    def queue_position_dict(self, d):
+        t = torch.tensor([int(d[i]) for i in range(self.queue_size)], dtype=torch.uint8)
+        if self._lru is None:
+            self._pending_qpos = t
+        else:
+            self.qpos.copy_(t.to(self.qpos.device))
+
+    def _labels_dev(self, lab, n):
+        t = torch.as_tensor(lab)
+        assert t.numel() == n, (t.numel(), n)
+        return t.to(device=self._dev, dtype=torch.int64, non_blocking=True).contiguous()
+
+    # -- one head pass ------------------------------------------------------------------------------
+    def _pass(self, p, g, probe_label, gallery_label, commit):
+        self._ensure()
+        lib, dev = self._lib, self._dev
+        Q, D = self.queue_size, self.feat_dim
+        B = p.shape[0]
+        assert p.shape == (B, D) and g.shape == (B, D), (p.shape, g.shape)
+        assert 1 <= B <= self.max_batch, f'batch {B} > max_batch {self.max_batch}'
+        assert self.queue.is_contiguous()
+        p32 = p.to(device=dev, dtype=torch.float32).contiguous()
+        g32 = g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        kg = self._labels_dev(gallery_label, B)
+        kp = self._labels_dev(probe_label, B)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            self.n_ones.zero_()
+            # ffc.py:162-177 / 214-235: LRU get/try_get + row/col bookkeeping, on the device
+            self._lru.assign(kg, journal=not commit, qpos=self.qpos, rows=self.rows, cols=self.cols, ones_list=self.ones_list,
+                            n_ones=self.n_ones, cmask=self.cmask)
+            # ffc.py:179-182 / 237-241: enqueue (fp32 queue + bf16 mirror), old rows saved on a rollback pass
+            check(lib.ffc_queue_scatter(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                        g32.data_ptr(), B, Q, D, None if commit else self.undo_rows.data_ptr(), s))
+            # ffc.py:189-194 / 242-246: probe labels after this pass's inserts
+            self._lru.view_batch(kp, self.label)
+            st = self.stats
+            hp = HeadPass(p32.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.label.data_ptr(),
+                          self.ones_list.data_ptr(), self.n_ones.data_ptr(), self.cmask.data_ptr(), B)
+            hs = HeadStats(*(self._stat_ptr(name, B) for name in ('lsum', 'osum', 'tgt', 'topv', 'topi')))
+            self.loss_buf.zero_()
+            dp = torch.empty(B, D, dtype=torch.float32, device=dev)
+            # ffc.py:195-202 / 248-254 + backward
+            check(lib.ffc_head_sweep(self._h, C.byref(hp), C.byref(hs), s))
+            check(lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), 1, self.loss_buf.data_ptr(), dp.data_ptr(), s))
+            loss = self.loss_buf[0].clone()
+            if not commit:   # ffc.py:255-259
+                check(lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                            self.undo_rows.data_ptr(), B, Q, D, s))
+                self._lru.undo(B, self.qpos)
+            self.cmask.zero_()
+            self._last = dict(rows=self.rows[:B], cols=self.cols[:B], label=self.label[:B], ones=self.ones_list, n_ones=self.n_ones)
+        return loss, dp
+
+    def _stat_ptr(self, name, B):
+        # the stats arrays are laid out [slots][n_rows][...] for the n_rows of THIS pass: use compact per-pass views
+        t = self.stats[name]
+        if B == t.shape[1]:
+            return t.data_ptr()
+        c = self._compact.get((name, B))
+        if c is None:
+            c = torch.empty((t.shape[0], B) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+            self._compact[(name, B)] = c
+        return c.data_ptr()
+
+    def head(self, p, g, probe_label, gallery_label, commit=True):
+        """One head pass: ``forward_impl`` (commit=True, ffc.py:153-204) or ``forward_impl_rollback`` (commit=False,
+        ffc.py:208-260) with embeddings in.  Returns the loss; gradients flow to ``p`` only."""
+        return _HeadFn.apply(p, self, g, probe_label, gallery_label, commit)
+
+    def last_bookkeeping(self):
+        """(rows, cols, labels, ones) of the most recent pass as Python lists (debug / parity tests; synchronises)."""
+        l = self._last
+        n1 = int(l['n_ones'].item())
+        return (l['rows'].tolist(), l['cols'].tolist(), l['label'].tolist(), sorted(l['ones'][:n1].tolist()))
+
+
+class FFC(FFCHead):
+    """ffc.py:10-267.  Buffers ``queue`` / ``mask`` live on this module, as in the reference state_dict."""
+
+    def __init__(self, net_type, feat_dim, queue_size=7409, scale=32.0, loss_type='AM', margin=0.4, momentum=0.99,
+                 neg_margin=0.25, pretrained_model_path=None, num_class=None, *, precision='bf16', max_batch=1024,
+                 probe_net=None, gallery_net=None):
+        FFCHead.__init__(self, feat_dim, queue_size, scale, loss_type, margin, precision=precision, max_batch=max_batch)
+        self.probe_net = probe_net if probe_net is not None else create_net(net_type, feat_dim=feat_dim, fp16=True)
+        self.gallery_net = gallery_net if gallery_net is not None else create_net(net_type, feat_dim=feat_dim, fp16=True)
+        self.neg_margin = neg_margin          # stored, unused (as in the reference, ffc.py:44)
+        self.m = momentum
+        self.mask_svfc = 1.2
+        for param_p, param_g in zip(self.probe_net.parameters(), self.gallery_net.parameters()):   # ffc.py:53-55
+            param_g.data.copy_(param_p.data)
+            param_g.requires_grad = False
+
+    @torch.no_grad()
+    def _momentum_update_gallery(self):
+        """ffc.py:139-145, as two multi-tensor ops instead of three kernels per parameter."""
+        pg = [q for q in self.gallery_net.parameters()]
+        pp = [q.data for q in self.probe_net.parameters()]
+        if pg:
+            torch._foreach_mul_(pg, self.m)
+            torch._foreach_add_(pg, pp, alpha=1.0 - self.m)
+
+    def forward_impl(self, p_data, g_data, probe_label, gallery_label):            # ffc.py:153-204
+        p = self.probe_net(p_data)
+        with torch.no_grad():
+            g = self.gallery_net(g_data)
+        return self.head(p, g, probe_label, gallery_label, commit=True)
+
+    def forward_impl_rollback(self, p_data, g_data, probe_label, gallery_label):   # ffc.py:208-260
+        p = self.probe_net(p_data)
+        with torch.no_grad():
+            self._momentum_update_gallery()
+            g = self.gallery_net(g_data)
+        return self.head(p, g, probe_label, gallery_label, commit=False)
+
+    def forward(self, x, y, x_label, y_label):                                     # ffc.py:264-267
+        loss2 = self.forward_impl_rollback(x, y, x_label, y_label)
+        loss1 = self.forward_impl(y, x, y_label, x_label)
+        return loss1 + loss2
