@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the FFC head hot path (BASELINE.json metric: head fwd+bwd samples/s, % of bf16 tensor peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2] [--impl ours|reference]
+
+A *step* is one reference ``FFC.forward`` over one synthetic batch, embeddings in: a rollback head pass
+(probe=x, gallery=y) plus a commit head pass (probe=y, gallery=x) -- ffc.py:264-267 -- i.e. 2*B probe rows
+("samples") per GPU, each through LRU bookkeeping, enqueue scatter, the fused margin-softmax sweep (loss and
+dEmb, both add_margin terms) and, on the rollback pass, the restore.  Workloads:
+  c3 (default)  B=1024 rows/GPU, 1,048,576 identities, queue 1,048,576 (column-sharded over N GPUs), D=512, Arc
+  c2            B=512, 100k identities, queue 65,536, D=512, Arc (single GPU)
+`value` is device-timed with the inputs resident in HBM; `e2e` is the same metric through the public
+``FFCHead.head`` API from pinned host buffers (H2D of embeddings+labels and a D2H read of the loss inside the
+timed region).  `--impl reference` times the reference algorithm's CPU port (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'very-large-scale-face-recognition_b200'))
+
+WORKLOADS = {
+    'c3': dict(name='C3: FFC head only, 512-d embeddings, batch 1024/GPU, 1M identities, queue 1M', B=1024, N=1 << 20, Q=1 << 20, D=512,
+               loss_type='Arc', margin=0.5, scale=32.0),
+    'c2': dict(name='C2: FFC head, batch 512, 100k identities, queue 64k, D=512', B=512, N=100000, Q=65536, D=512,
+               loss_type='Arc', margin=0.5, scale=32.0),
+}
+CPU_SAMPLE = dict(B=256, Q=32768)   # bounded CPU sample: rows per pass and queue slice; scaled linearly in Q
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(burst=d['bf16_tflops'], sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']), hbm=d['hbm_gbs'], src='measured')
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src='fallback')
+
+
+def make_batches(w, n_batches, seed, rank=0, world=1):
+    """id half = chunks of a seeded permutation (same ids in x and y), instance halves iid uniform."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed + 7919 * rank)
+    B, N, D = w['B'], w['N'], w['D']
+    h = B // 2
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(seed))
+    out = []
+    for s in range(n_batches):
+        base = ((s * world + rank) * h) % max(1, N - h)
+        ids = perm[base:base + h]
+        xl = torch.cat([ids, torch.randint(0, N, (B - h,), generator=g)])
+        yl = torch.cat([ids, torch.randint(0, N, (B - h,), generator=g)])
+        x = F.normalize(torch.randn(B, D, generator=g))
+        y = F.normalize(torch.randn(B, D, generator=g))
+        out.append((x, y, xl, yl))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the reference algorithm's port (oracle/head_ref.py) on the host cores, bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(w, steps, warmup):
+    import torch
+    from oracle.head_ref import HeadOracle
+    Bs, Qs = min(CPU_SAMPLE['B'], w['B']), min(CPU_SAMPLE['Q'], w['Q'])
+    ws = dict(w, B=Bs, N=max(Qs, int(w['N'] * Qs / w['Q'])), Q=Qs)
+    o = HeadOracle(w['D'], Qs, w['scale'], w['loss_type'], w['margin'], dtype=torch.float32)
+    o.lru.restore([(i, i) for i in range(Qs)])
+    batches = make_batches(ws, 4, seed=1234)
+    times = []
+    for s in range(warmup + steps):
+        x, y, xl, yl = batches[s % len(batches)]
+        x = x.clone().requires_grad_(True)
+        y = y.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        loss = o.forward(x, y, xl.tolist(), yl.tolist())
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    raw = 2 * Bs / t                               # samples/s at the sample's queue size
+    scaled = raw * Qs / w['Q']                     # per-sample cost is linear in Q
+    sample = (f'oracle port (torch fp32, materialised B x Q logits, argsort top-k, autograd backward) on B={Bs} rows/pass, '
+              f'queue {Qs}, D={w["D"]}: {t * 1e3:.0f} ms/step = {raw:.0f} samples/s, scaled by {Qs}/{w["Q"]} to the full queue')
+    return dict(value=scaled, unit='samples/s', cores=torch.get_num_threads(), kind='port', sample=sample), t
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, t = cpu_reference(w, max(1, args.steps), max(0, args.warmup))
+    line = dict(metric='ffc_head_fwd_bwd_samples_per_s', value=cb['value'], unit='samples/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=w['name'], loss='Arc', margin=w['margin'], scale=w['scale']), cpu_baseline=cb,
+                e2e=dict(value=cb['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[4:8]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if sm:
+            sm.sort()
+            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    import ffc_b200
+    from ffc_b200 import _capi
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _capi.lib()
+    B, N, Q, D = w['B'], w['N'], w['Q'], w['D']
+
+    if world == 1:
+        head = ffc_b200.FFCHead(D, Q, w['scale'], w['loss_type'], w['margin'], precision='bf16', max_batch=B, device=dev)
+        head._ensure()
+        # steady state: LRU full: ids 0..Q-1 resident, slot i <- id i, recency = id order
+        head._lru.restore_arrays(torch.arange(Q, dtype=torch.int64), torch.arange(Q, dtype=torch.int32))
+
+        def step(x, y, xl, yl):
+            l2, d2 = head._pass(x, y, xl, yl, False)
+            l1, d1 = head._pass(y, x, yl, xl, True)
+            return l1 + l2
+
+        def step_api(x, y, xl, yl):      # public API, gradients requested
+            x = x.requires_grad_(True)
+            y = y.requires_grad_(True)
+            loss = head.head(x, y.detach(), xl, yl, commit=False) + head.head(y, x.detach(), yl, xl, commit=True)
+            return loss
+    else:
+        from ffc_b200.dist import ShardedFFCHead
+        head = ShardedFFCHead(D, Q, w['scale'], w['loss_type'], w['margin'], max_batch=B, device=dev)
+        head.prefill_identity(N)
+
+        def step(x, y, xl, yl):
+            l2, d2 = head.head_pass(x, y, xl, yl, False)
+            l1, d1 = head.head_pass(y, x, yl, xl, True)
+            return l1 + l2
+        step_api = step
+
+    n_b = 6
+    host = make_batches(w, n_b, seed=1234, rank=rank, world=world)
+    pinned = [tuple(t.pin_memory() for t in b) for b in host]
+    devb = [(x.to(dev), y.to(dev), xl.to(dev), yl.to(dev)) for x, y, xl, yl in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ----
+    for s in range(args.warmup):
+        step(*devb[s % n_b])
+    barrier()
+    clocks = Clocks(local) if rank == 0 else None
+    head.set_timing(True)
+    l0 = lib.ffc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        loss = step(*devb[(args.warmup + s) % n_b])
+    e1.record()
+    barrier()
+    launches = lib.ffc_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    sweep_ms, sweep_n = head.get_timing()
+    head.set_timing(False)
+    clk = clocks.stop() if clocks else None
+    loss_val = float(loss)
+
+    # ---- end to end through the public API from pinned host buffers (e2e) ----
+    for s in range(max(1, args.warmup // 2)):
+        x, y, xl, yl = pinned[s % n_b]
+        float(step_api(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), xl, yl))
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.steps):
+        x, y, xl, yl = pinned[(args.warmup + s) % n_b]
+        lv = float(step_api(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), xl, yl))   # D2H read of the loss
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    t_all = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t_all[0]), float(t_all[1])
+    samples = 2 * B * world * args.steps
+    value = samples / (ms * 1e-3)
+    pk = peaks()
+    rows_per_sweep = B * world
+    q_local = Q // world
+    flops = 4.0 * rows_per_sweep * q_local * D                     # algorithmic FLOPs of one main sweep launch (4*B*Q*D)
+    ach = flops * sweep_n / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
+    if rank == 0:
+        cb, _ = cpu_reference(w, 2, 1) if world == 1 and not args.no_cpu else (None, None)
+        line = dict(metric='ffc_head_fwd_bwd_samples_per_s', value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
+                    config=dict(workload=w['name'], rows_per_pass_per_gpu=B, passes_per_step=2, identities=N, queue=Q, feat_dim=D, loss=w['loss_type'],
+                                margin=w['margin'], scale=w['scale'], sharding=('none' if world == 1 else f'queue columns /{world}'),
+                                l2_policy='working set (bf16 queue %.0f MB per rank) exceeds the 126 MB L2' % (q_local * D * 2 / 1e6)),
+                    e2e=dict(value=samples / (ms_e2e * 1e-3), unit='samples/s', h2d_bytes_per_step=2 * B * D * 4 + 2 * B * 8, d2h_bytes_per_step=4,
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(launches),
+                    roofline=dict(bound='tensor', achieved=ach, peak=pk['sustained'], unit='TFLOP/s', frac=ach / pk['sustained'], traffic=None,
+                                  kernel='ffc_head_sweep_sm100_kernel (main sweep)', launches=int(sweep_n), avg_ms=sweep_ms / max(1, sweep_n),
+                                  algorithmic_flops_per_launch=flops, peak_kind=f'bf16_tflops_sustained ({pk["src"]})',
+                                  frac_of_burst=ach / pk['burst'], sweep_share_of_step=sweep_ms / ms),
+                    clocks=clk, loss=loss_val)
+        if cb is not None:
+            line['cpu_baseline'] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == '__main__':
+    main()

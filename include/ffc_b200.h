@@ -147,7 +147,7 @@ typedef struct ffc_head_pass {
   const float* queue_f32;      /* [2, q_local, D] */
   const void* queue_bf16;      /* [2, q_local, D] bf16 mirror (bf16 path) */
   const int32_t* label;        /* [n_rows] global slot or -1 (ffc.py:194/246) */
-  const int32_t* ones_list;    /* [<= max_rows] GLOBAL slots hit in this pass's bookkeeping (ffc.py:197) */
+  const int32_t* ones_list;    /* [<= max_rows] LOCAL slots hit in this pass's bookkeeping (ffc.py:197) */
   const int32_t* n_ones;       /* device scalar */
   const uint32_t* cmask;       /* bitmask over LOCAL slots: bit set <=> slot in ones_list; may be NULL iff n_ones==0 always */
   int32_t n_rows;
@@ -155,8 +155,9 @@ typedef struct ffc_head_pass {
 
 /* Rank-local statistics produced by the sweep, consumed by finalize.  Layout (all fp32 unless
  * noted), n = n_rows, k = topk, D = feat_dim:
- *   lsum   [3][n]      softmax denominators (relative to the fixed max m = c*scale): common, side0, side1
- *   osum   [3][n][D]   sum_j p~_ij W_j for the same three column sets
+ *   lsum   [4][n]      softmax denominators (relative to the fixed max M = c*scale): common under loss 1,
+ *                      common under loss 2 (differs only for SV), side0 (`ones` rows of queue[0]), side1 (queue[1])
+ *   osum   [4][n][D]   sum_j p~_ij W_j for the same four column sets
  *   tgt    [4][n]      cos_t under queue[0], cos_t under W2, (owner flag as 1.0/0.0), spare
  *   topv   [3][n][k]   running top-k cosines (descending; -inf padded), topi int32 [3][n][k] GLOBAL slots
  * On several GPUs the caller sums lsum/tgt across ranks (all-reduce), all-gathers topv/topi, then
@@ -181,6 +182,12 @@ int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_sta
 
 /* sizes in bytes of the five stats arrays for n rows (one rank's worth) */
 int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]);
+
+/* Roofline evidence: when enabled, every MAIN sweep launch (the tcgen05 kernel over queue[0]) is
+ * bracketed by CUDA events on its launch stream; get_timing (host-sync) returns the summed device
+ * time in ms and the number of launches since set_timing(1). */
+int ffc_head_set_timing(ffc_head_t* h, int enable);
+int ffc_head_get_timing(ffc_head_t* h, double* total_ms_out, int64_t* launches_out);
 
 /* Debug / evidence: number of kernel launches issued by this library since load. */
 int64_t ffc_launch_count(void);

@@ -11,6 +11,7 @@
 // Hard negatives (ffc.py:86-92): mean over outlier rows and their top-k cosines of max(cos, 0).
 #include <algorithm>
 #include <math.h>
+#include <vector>
 
 #include "head_internal.cuh"
 
@@ -33,6 +34,10 @@ struct ffc_head {
   float* topv_part;
   int32_t* topi_part;
   ffc::Sm100Cache* sm100;
+  // optional device timing of the main sweep kernel (bench / roofline evidence)
+  int timing;
+  std::vector<cudaEvent_t>* ev;   // pairs (start, stop), recorded on the launch stream
+  size_t ev_used;
 };
 
 namespace ffc {
@@ -530,6 +535,7 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_CUDA(cudaMalloc(&h->topv_part, h->part_rows_cap * KMAX * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->topi_part, h->part_rows_cap * KMAX * sizeof(int32_t)));
   if (cfg->precision == FFC_PREC_BF16) h->sm100 = sm100_cache_create();
+  h->ev = new std::vector<cudaEvent_t>();
   *out = h;
   return FFC_OK;
 }
@@ -550,6 +556,10 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
   cudaFree(h->topv_part);
   cudaFree(h->topi_part);
   if (h->sm100) sm100_cache_destroy(h->sm100);
+  if (h->ev) {
+    for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
+    delete h->ev;
+  }
   delete h;
   return FFC_OK;
 }
@@ -564,8 +574,23 @@ static int run_one_sweep(ffc_head* h, SweepArgs a, int cache_slot, int stat_slot
   a.o_part = h->o_part;
   a.topv_part = h->topv_part;
   a.topi_part = h->topi_part;
+  const bool timed = h->timing && cache_slot == 0;
+  if (timed) {
+    if (h->ev_used + 2 > h->ev->size()) {
+      for (int e = 0; e < 2; ++e) {
+        cudaEvent_t ev;
+        FFC_CUDA(cudaEventCreate(&ev));
+        h->ev->push_back(ev);
+      }
+    }
+    FFC_CUDA(cudaEventRecord((*h->ev)[h->ev_used], s));
+  }
   int rc = bf16 ? launch_sweep_sm100(h->sm100, cache_slot, a, s) : launch_sweep_simt(a, s);
   if (rc) return rc;
+  if (timed) {
+    FFC_CUDA(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
+    h->ev_used += 2;
+  }
   const int n = a.n_rows, D = a.D, k = a.k;
   head_reduce_kernel<<<n, 128, 0, s>>>(a.l_part, a.o_part, a.topv_part, a.topi_part, a.n_chunks, n, D, k, out->lsum + (int64_t)stat_slot * n,
                                        out->osum + (int64_t)stat_slot * n * D, top_slot >= 0 ? out->topv + (int64_t)top_slot * n * k : nullptr,
@@ -684,5 +709,26 @@ extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const f
   FFC_LAUNCH_CHECK();
   head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
   FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_set_timing(ffc_head_t* h, int enable) {
+  FFC_REQUIRE(h != nullptr, "ffc_head_set_timing: NULL handle");
+  h->timing = enable ? 1 : 0;
+  h->ev_used = 0;
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_get_timing(ffc_head_t* h, double* total_ms_out, int64_t* launches_out) {
+  FFC_REQUIRE(h && total_ms_out && launches_out, "ffc_head_get_timing: NULL argument");
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    FFC_CUDA(cudaEventSynchronize((*h->ev)[i + 1]));
+    float ms = 0.f;
+    FFC_CUDA(cudaEventElapsedTime(&ms, (*h->ev)[i], (*h->ev)[i + 1]));
+    tot += ms;
+  }
+  *total_ms_out = tot;
+  *launches_out = (int64_t)(h->ev_used / 2);
   return FFC_OK;
 }

@@ -71,7 +71,7 @@ class _HeadFn(torch.autograd.Function):
 class FFCHead(Module):
     """State and kernels of the FFC head: prototype queue [2,Q,D] (+ bf16 mirror), device LRU, queue positions."""
 
-    def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024):
+    def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024, device=None):
         super().__init__()
         assert loss_type in ('AM', 'Arc', 'SV')
         assert precision in _capi.PRECISIONS
@@ -80,8 +80,10 @@ class FFCHead(Module):
         self.precision = precision
         self.hard_neg = hard_neg_k(self.queue_size)
         self.max_batch = int(max_batch)
-        self.register_buffer('queue', F.normalize(torch.rand(2, self.queue_size, self.feat_dim), dim=2))   # ffc.py:29-30
-        self.register_buffer('mask', torch.zeros(self.queue_size, 1))                                       # ffc.py:45
+        q = torch.rand(2, self.queue_size, self.feat_dim, device=device)                                     # ffc.py:29-30
+        q /= q.norm(dim=2, keepdim=True).clamp_min(1e-12)
+        self.register_buffer('queue', q)
+        self.register_buffer('mask', torch.zeros(self.queue_size, 1, device=device))                        # ffc.py:45
         self._dev = None
         self._lru = None
         self._compact = {}
@@ -145,6 +147,16 @@ class FFCHead(Module):
         """The device LRU (reference attribute ``ffc_net.lru``, main.py:85); created on first use."""
         self._ensure()
         return self._lru
+
+    def set_timing(self, enable):
+        """Bracket every main-sweep launch with CUDA events (roofline evidence for bench.py)."""
+        self._ensure()
+        check(self._lib.ffc_head_set_timing(self._h, 1 if enable else 0))
+
+    def get_timing(self):
+        ms, n = C.c_double(), C.c_int64()
+        check(self._lib.ffc_head_get_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def sync_mirror(self):
         """Refresh the bf16 mirror from the fp32 queue (after construction / checkpoint load)."""
@@ -244,8 +256,8 @@ class FFC(FFCHead):
 
     def __init__(self, net_type, feat_dim, queue_size=7409, scale=32.0, loss_type='AM', margin=0.4, momentum=0.99,
                  neg_margin=0.25, pretrained_model_path=None, num_class=None, *, precision='bf16', max_batch=1024,
-                 probe_net=None, gallery_net=None):
-        FFCHead.__init__(self, feat_dim, queue_size, scale, loss_type, margin, precision=precision, max_batch=max_batch)
+                 probe_net=None, gallery_net=None, device=None):
+        FFCHead.__init__(self, feat_dim, queue_size, scale, loss_type, margin, precision=precision, max_batch=max_batch, device=device)
         self.probe_net = probe_net if probe_net is not None else create_net(net_type, feat_dim=feat_dim, fp16=True)
         self.gallery_net = gallery_net if gallery_net is not None else create_net(net_type, feat_dim=feat_dim, fp16=True)
         self.neg_margin = neg_margin          # stored, unused (as in the reference, ffc.py:44)

@@ -123,6 +123,13 @@ class LRU:
         slots = torch.tensor([int(v) for _, v in kvs], dtype=torch.int32)
         check(self._lib.ffc_lru_import(self._h, keys.data_ptr(), slots.data_ptr(), len(kvs), self._s()))
 
+    def restore_arrays(self, keys, slots):
+        """restore() from CPU int64 / int32 tensors (most- to least-recent), for large caches."""
+        keys = keys.to(dtype=torch.int64, device='cpu').contiguous()
+        slots = slots.to(dtype=torch.int32, device='cpu').contiguous()
+        assert keys.numel() == slots.numel() <= self.capacity
+        check(self._lib.ffc_lru_import(self._h, keys.data_ptr(), slots.data_ptr(), keys.numel(), self._s()))
+
     def __iter__(self):          # lru.py:94-98
         return iter(self.state_dict())
 
