@@ -117,7 +117,7 @@ class Clocks:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             pass
@@ -198,7 +198,9 @@ def run_ours(args, w):
             return l1 + l2
         step_api = step
 
-    n_b = 6
+    # one distinct batch per step: re-feeding an embedding that is already in the queue makes the target cosine
+    # exactly 1, the reference's Arc NaN hazard
+    n_b = args.steps + args.warmup
     host = make_batches(w, n_b, seed=1234, rank=rank, world=world)
     pinned = [tuple(t.pin_memory() for t in b) for b in host]
     devb = [(x.to(dev), y.to(dev), xl.to(dev), yl.to(dev)) for x, y, xl, yl in host]
@@ -209,10 +211,10 @@ def run_ours(args, w):
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value) ----
+    clocks = Clocks(local) if rank == 0 else None
     for s in range(args.warmup):
         step(*devb[s % n_b])
     barrier()
-    clocks = Clocks(local) if rank == 0 else None
     head.set_timing(True)
     l0 = lib.ffc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,16 +231,14 @@ def run_ours(args, w):
     loss_val = float(loss)
 
     # ---- end to end through the public API from pinned host buffers (e2e) ----
-    for s in range(max(1, args.warmup // 2)):
-        x, y, xl, yl = pinned[s % n_b]
-        float(step_api(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), xl, yl))
+    pinned = pinned[::-1]     # other embeddings than the ones just enqueued
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for s in range(args.steps):
         x, y, xl, yl = pinned[(args.warmup + s) % n_b]
-        lv = float(step_api(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), xl, yl))   # D2H read of the loss
+        lv = float(step_api(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True), xl, yl).detach())   # D2H read of the loss
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -279,7 +279,7 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])

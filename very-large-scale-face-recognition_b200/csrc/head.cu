@@ -393,7 +393,11 @@ __global__ void __launch_bounds__(128) head_finalize_kernel(const FinalizeArgs a
     if (!outl) {
       const double s = a.scale, M = a.fixed_max, m = a.margin;
       for (int l = 0; l < 2; ++l) {
-        const double ct = a.tgt[l * n + i];
+        double ct = a.tgt[l * n + i];
+        // bf16 operands are rounded, so a cosine of two (nearly) identical unit vectors can land a few ulp outside
+        // [-1, 1] and turn ffc.py:101's sqrt into NaN where the fp32 reference is finite: keep it strictly inside.
+        // The fp32 check mode does not clamp and propagates NaN exactly like the reference.
+        if (a.use_bf16_rows) ct = fmin(fmax(ct, -1.0 + 1e-6), 1.0 - 1e-6);
         double ft, dft;
         if (a.loss_type == FFC_LOSS_AM) {
           ft = ct - m;

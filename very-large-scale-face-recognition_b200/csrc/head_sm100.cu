@@ -16,7 +16,7 @@
 //
 // Executed tensor FLOPs == algorithmic FLOPs (4 * rows * cols * D): no recompute, no B x Q logits.
 // Synchronisation is all mbarriers: TMA -> MMA (full/empty rings), MMA -> epilogue (tcgen05.commit),
-// epilogue -> peer MMA (remote mbarrier arrive), peer MMA -> epilogue (commit + relay warp).
+// epilogue -> peer MMA (st.async complete_tx on the peer's mbarrier), peer MMA -> epilogue (multicast tcgen05.commit).
 #include <cuda.h>
 
 #include <mutex>
@@ -29,7 +29,9 @@ namespace ffc {
 constexpr int BM = 128;            // probe rows per item
 constexpr int BN = 128;            // queue rows per tile
 constexpr int KC = 64;             // bf16 elements per 128-byte swizzle row
-constexpr int NS1 = 4;             // S-CTA W K-chunk stages (16 KB each)
+constexpr int NS1 = 6;             // S-CTA W K-chunk stages (16 KB each)
+constexpr int NSB = 4;             // S accumulators in the S-CTA's TMEM (4 x 128 columns)
+constexpr int NPB = 3;             // P~ buffers in the O-CTA's shared memory
 constexpr int JB = 32;             // queue rows per O-CTA W stage
 constexpr int NTHREADS = 384;      // 12 warps
 constexpr int CHUNK1_BYTES = BN * KC * 2;   // 16384
@@ -38,18 +40,17 @@ constexpr float LOG2E = 1.4426950408889634f;
 // ---- shared memory map (same for both roles; 1024-byte aligned base) ----
 // [0, 1024)                 barriers, tmem base, small staging
 // S-CTA: [1024, +D/64*16K)  P tile (K-major SW128 chunks)      then NS1 x 16 KB W chunk ring
-// O-CTA: [1024, +64K)       P~ buffers 2 x 32 KB               then NS2 x (D/64 * 4 KB) W stage ring
+// O-CTA: [1024, +96K)       P~ buffers 3 x 32 KB               then NS2 x (D/64 * 4 KB) W stage ring
 constexpr int OFF_DATA = 1024;
 constexpr int PT_BYTES = BM * BN * 2;       // 32768 per P~ buffer
 
 struct Bars {   // all in the first 1024 bytes
   uint64_t p_full;
   uint64_t w_full[NS1], w_empty[NS1];
-  uint64_t s_full[2], s_empty[2];
-  uint64_t pt_empty[2];            // S-CTA side: P~ buffer g may be overwritten
+  uint64_t s_full[NSB], s_empty[NSB];
+  uint64_t pt_empty[NPB];          // S-CTA side: P~ buffer b may be overwritten (signalled by the peer's tcgen05.commit)
   uint64_t w2_full[8], w2_empty[8];
-  uint64_t pt_full[2];             // O-CTA side: P~ buffer g is complete
-  uint64_t pt_free_local[2];       // O-CTA side: GEMM-2 finished reading P~ buffer g
+  uint64_t pt_full[NPB];           // O-CTA side: P~ buffer b is complete (st.async complete_tx, 32 KB per tile)
   uint64_t o_full;
   uint32_t tmem_base;
   uint32_t pad;
@@ -145,6 +146,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -155,8 +165,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// asynchronous 16-byte store into the peer CTA's shared memory; completion is counted (complete_tx) on the
+// peer's mbarrier, so the writer needs no fence / drain before the consumer may be released
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(a), "r"(b),
+               "r"(c), "r"(d), "r"(mbar)
+               : "memory");
+}
+// tcgen05.commit that arrives on the barrier at the same offset in the CTAs of `cta_mask`
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {   // long waits: back off instead of spinning
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    asm volatile("nanosleep.u32 2000;");
+  }
 }
 
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): SWIZZLE_128B, version 1
@@ -221,7 +258,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   unsigned char* sP = smem + OFF_DATA;                         // S-CTA
   unsigned char* sW1 = sP + nkc * CHUNK1_BYTES;                // S-CTA
   unsigned char* sPt = smem + OFF_DATA;                        // O-CTA
-  unsigned char* sW2 = sPt + 2 * PT_BYTES;                     // O-CTA
+  unsigned char* sW2 = sPt + NPB * PT_BYTES;                   // O-CTA
 
   if (threadIdx.x == 0) {
     mbar_init(&bars.p_full, 1);
@@ -229,12 +266,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSB; ++i) {
       mbar_init(&bars.s_full[i], 1);
       mbar_init(&bars.s_empty[i], 4);
+    }
+    for (int i = 0; i < NPB; ++i) {
       mbar_init(&bars.pt_empty[i], 1);
-      mbar_init(&bars.pt_full[i], 4);
-      mbar_init(&bars.pt_free_local[i], 1);
+      mbar_init(&bars.pt_full[i], 1);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bars.w2_full[i], 1);
@@ -244,8 +282,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    // S-CTA: 2 x 128 columns of S; O-CTA: D columns of O (power of two >= 32)
-    const uint32_t ncols = rank == 0 ? 256u : (uint32_t)(D < 32 ? 32 : D);
+    // S-CTA: NSB x 128 columns of S; O-CTA: D columns of O (power of two >= 32)
+    const uint32_t ncols = rank == 0 ? (uint32_t)(NSB * BN) : (uint32_t)(D < 32 ? 32 : D);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -254,7 +292,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars.tmem_base);
-
   if (rank == 0) {
     // =========================================== S-CTA ===========================================
     if (warp == 0) {
@@ -283,11 +320,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         int stage = 0;
         uint32_t ph = 0;
         for (int i = 0; i < n_tiles; ++i) {
-          const int g = i & 1;
-          const uint32_t use = (uint32_t)(i >> 1);
-          mbar_wait(&bars.s_empty[g], (use & 1) ^ 1);
+          const int sb = i & (NSB - 1);
+          const uint32_t use = (uint32_t)(i / NSB);
+          mbar_wait(&bars.s_empty[sb], (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t tmem_s = tmem_base + (uint32_t)(g * BN);
+          const uint32_t tmem_s = tmem_base + (uint32_t)(sb * BN);
           for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(&bars.w_full[stage], ph);
             tc_fence_after();
@@ -303,11 +340,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               ph ^= 1;
             }
           }
-          tc_commit(&bars.s_full[g]);
+          tc_commit(&bars.s_full[sb]);
         }
       }
     } else if (warp >= 4) {
-      // ---- epilogue: warpgroup g owns S buffer g, P~ buffer g and the tiles of parity g ----
+      // ---- epilogue: warpgroup g takes the tiles of parity g (S buffer i%4, P~ buffer i%3) ----
       const int g = (warp - 4) >> 2;
       const int q4 = warp & 3;                    // TMEM lane quarter
       const int r_local = q4 * 32 + lane;         // row within the item
@@ -329,37 +366,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         ti[q] = -1;
       }
       float kth = -INFINITY;
-      const uint32_t pt_remote = map_to_rank(smem_u32(smem + OFF_DATA + g * PT_BYTES), 1);
-      const uint32_t ptfull_remote = map_to_rank(smem_u32(&bars.pt_full[g]), 1);
+      const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
+      const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
       const uint32_t sw = (uint32_t)(r_local & 7);
       for (int i = g; i < n_tiles; i += 2) {
-        const uint32_t use = (uint32_t)(i >> 1);
+        const int sb = i & (NSB - 1);
+        const int pb = i % NPB;
         const int j0 = (t_begin + i) * BN;
-        mbar_wait(&bars.s_full[g], use & 1);
+        // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
+        uint4 cm = make_uint4(0u, 0u, 0u, 0u);
+        if (prm.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(prm.cmask + (j0 >> 5)));
+        mbar_wait(&bars.s_full[sb], (uint32_t)(i / NSB) & 1);
         tc_fence_after();
-        mbar_wait_cluster(&bars.pt_empty[g], (use & 1) ^ 1);
-        const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(g * BN);
+        mbar_wait(&bars.pt_empty[pb], ((uint32_t)(i / NPB) & 1) ^ 1);
+        const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
+        const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
+        const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t v[32];
-          tc_ld32(tmem_s + cc * 32, v);
-          const int col0 = j0 + cc * 32;
-          uint32_t excl = (prm.cmask && col0 < n_cols) ? __ldg(prm.cmask + (col0 >> 5)) : 0u;
+        for (int cc = 0; cc < BN / 16; ++cc) {
+          uint32_t v[16];
+          tc_ld16(tmem_s + cc * 16, v);
+          const int col0 = j0 + cc * 16;
+          const uint32_t cw = (cc >> 1) == 0 ? cm.x : (cc >> 1) == 1 ? cm.y : (cc >> 1) == 2 ? cm.z : cm.w;
+          uint32_t excl = (cw >> ((cc & 1) * 16)) & 0xffffu;
           const int trel = tcol - col0;
-          if ((unsigned)trel < 32u) excl |= 1u << trel;
-          if ((int64_t)col0 + 32 > n_cols) {
+          if ((unsigned)trel < 16u) excl |= 1u << trel;
+          if ((int64_t)col0 + 16 > n_cols) {
             const int nv = (int)(n_cols - col0);   // valid columns in this chunk (may be <= 0)
-            excl |= nv <= 0 ? 0xffffffffu : (0xffffffffu << nv);
+            excl |= nv <= 0 ? 0xffffu : (0xffffu << nv) & 0xffffu;
           }
           const bool slow = __any_sync(0xffffffffu, excl != 0u);
           // hard-negative top-k on the raw cosines of outlier rows
           if (warp_out) {
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            for (int c = 0; c < 16; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
             if (outl && mx > kth) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
+              for (int c = 0; c < 16; ++c) {
                 const float x = __uint_as_float(v[c]);
                 if (x > kth && !((excl >> c) & 1u)) {
                   topk_insert<KMAX>(tv, ti, k, x, col0 + c);
@@ -370,62 +414,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               }
             }
           }
-          uint32_t pk[16];
-          if (!slow) {
+          uint32_t pk[8];
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
-              float p0, p1, g0, g1;
-              if (SV) {
-                const bool m0 = x0 > thr, m1 = x1 > thr;
-                p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
-                p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
-                g0 = m0 ? p0 * SV_T : p0;
-                g1 = m1 ? p1 * SV_T : p1;
-              } else {
-                p0 = g0 = ex2f(fmaf(x0, a2, -b2));
-                p1 = g1 = ex2f(fmaf(x1, a2, -b2));
-              }
-              lsum += p0 + p1;
-              pk[c >> 1] = pack_bf16(g0, g1);
+          for (int c = 0; c < 16; c += 2) {
+            float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
+            float p0, p1, g0, g1;
+            if (SV) {
+              const bool m0 = x0 > thr, m1 = x1 > thr;
+              p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
+              p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
+              g0 = m0 ? p0 * SV_T : p0;
+              g1 = m1 ? p1 * SV_T : p1;
+            } else {
+              p0 = g0 = ex2f(fmaf(x0, a2, -b2));
+              p1 = g1 = ex2f(fmaf(x1, a2, -b2));
             }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
-              float p0, p1, g0, g1;
-              if (SV) {
-                const bool m0 = x0 > thr, m1 = x1 > thr;
-                p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
-                p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
-                g0 = m0 ? p0 * SV_T : p0;
-                g1 = m1 ? p1 * SV_T : p1;
-              } else {
-                p0 = g0 = ex2f(fmaf(x0, a2, -b2));
-                p1 = g1 = ex2f(fmaf(x1, a2, -b2));
-              }
+            if (slow) {   // warp-uniform: only chunks that contain an excluded column pay for the per-element test
               if ((excl >> c) & 1u) p0 = g0 = 0.f;
               if ((excl >> (c + 1)) & 1u) p1 = g1 = 0.f;
-              lsum += p0 + p1;
-              pk[c >> 1] = pack_bf16(g0, g1);
             }
+            lsum += p0 + p1;
+            pk[c >> 1] = pack_bf16(g0, g1);
           }
-          // P~[r_local][cc*32 .. +32) as 4 x 16-byte chunks, K-major SWIZZLE_128B: 64-column sub-tiles of 16 KB
-          const uint32_t base = pt_remote + (uint32_t)((cc >> 1) * (BM * 128)) + (uint32_t)(r_local * 128);
+          // P~[r_local][cc*16 .. +16) as 2 x 16-byte chunks, K-major SWIZZLE_128B: 64-column sub-tiles of 16 KB.
+          // st.async: each 16-byte store counts itself on the peer's pt_full[pb] (32 KB per tile in total).
+          const uint32_t base = pt_remote + (uint32_t)((cc >> 2) * (BM * 128)) + (uint32_t)(r_local * 128);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t chunk16 = (uint32_t)((cc & 1) * 4 + q);
-            st_cluster_v4(base + ((chunk16 ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t chunk16 = (uint32_t)((cc & 3) * 2 + q);
+            st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        // S buffer g may be overwritten by the next-but-one tile's MMA
+        // S buffer sb may be overwritten by a later tile's MMA
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.s_empty[g]);
-        // publish P~ buffer g to the peer's tensor core (generic-proxy writes -> async-proxy reads)
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(ptfull_remote);
+        if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
       }
       // ---- per-row partials: combine the two warpgroups through shared memory ----
       float* stage_l = reinterpret_cast<float*>(smem + OFF_LSTAGE);               // [128]
@@ -493,12 +516,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         int stage = 0;
         uint32_t ph = 0;
         for (int i = 0; i < n_tiles; ++i) {
-          const int g = i & 1;
-          const uint32_t use = (uint32_t)(i >> 1);
-          mbar_wait_cluster(&bars.pt_full[g], use & 1);
+          const int pb = i % NPB;
+          const uint32_t use = (uint32_t)(i / NPB);
+          // this thread is the single arriver of pt_full[pb]; the 32 KB of P~ arrive as st.async complete_tx bytes
+          mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);
+          mbar_wait_cluster(&bars.pt_full[pb], use & 1);
           asm volatile("fence.proxy.async;" ::: "memory");
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sPt + g * PT_BYTES);
+          const uint32_t a_base = smem_u32(sPt + pb * PT_BYTES);
           for (int jb = 0; jb < BN / JB; ++jb) {
             mbar_wait(&bars.w2_full[stage], ph);
             tc_fence_after();
@@ -519,19 +544,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               ph ^= 1;
             }
           }
-          tc_commit(&bars.pt_free_local[g]);
+          tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);   // frees P~ buffer pb: arrives in the S-CTA (cluster rank 0)
         }
         tc_commit(&bars.o_full);
-      }
-    } else if (warp == 3) {
-      if (lane == 0) {
-        // relay "P~ buffer g is free" to the S-CTA
-        for (int i = 0; i < n_tiles; ++i) {
-          const int g = i & 1;
-          const uint32_t use = (uint32_t)(i >> 1);
-          mbar_wait(&bars.pt_free_local[g], use & 1);
-          mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[g]), 0));
-        }
       }
     } else if (warp >= 4) {
       // ---- O epilogue: TMEM -> global partial [chunk][row][D]; warpgroup g takes half of the columns ----
@@ -541,7 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const int row = row0 + r_local;
       const bool row_ok = row < prm.n_rows;
       if (n_tiles > 0) {
-        mbar_wait(&bars.o_full, 0);
+        mbar_wait_sleep(&bars.o_full, 0);
         tc_fence_after();
       }
       const int half = D / 2;                      // D is a multiple of 64
@@ -580,7 +595,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   __syncthreads();
   cluster_sync_all();     // the peer may still signal into this CTA's shared memory until here
   if (warp == 2) {
-    const uint32_t ncols = rank == 0 ? 256u : (uint32_t)(D < 32 ? 32 : D);
+    const uint32_t ncols = rank == 0 ? (uint32_t)(NSB * BN) : (uint32_t)(D < 32 ? 32 : D);
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
@@ -648,7 +663,7 @@ int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
 
 static int ns2_for(int D) {
   const int stage = (D / KC) * JB * KC * 2;
-  int ns = (int)((200 * 1024 - 2 * PT_BYTES) / stage);
+  int ns = (int)((200 * 1024 - NPB * PT_BYTES) / stage);
   return ns > 8 ? 8 : (ns < 2 ? 2 : ns);
 }
 
@@ -684,7 +699,7 @@ int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cu
   p.topi_part = a.topi_part;
   const int nkc = a.D / KC;
   const size_t smem_s = OFF_DATA + (size_t)nkc * CHUNK1_BYTES + (size_t)NS1 * CHUNK1_BYTES;
-  const size_t smem_o = OFF_DATA + 2 * (size_t)PT_BYTES + (size_t)p.ns2 * nkc * JB * KC * 2;
+  const size_t smem_o = OFF_DATA + NPB * (size_t)PT_BYTES + (size_t)p.ns2 * nkc * JB * KC * 2;
   const size_t smem = std::max(smem_s, smem_o) + 1024;   // slack for the 1024-byte alignment of the dynamic base
   FFC_REQUIRE(smem <= 227 * 1024, "tcgen05 sweep: shared memory budget exceeded (%zu bytes)", smem);
   if (!cache->attr_set) {
