@@ -70,17 +70,21 @@ int ffc_lru_clear(ffc_lru_t* h, void* stream);
  * ffc.py:165,176 `ones_idx`.  qpos_dev (uint8[capacity]) is ffc.py:41-43 queue_position_dict; pass
  * NULL for a plain LRU (rows_out is then 0 for misses and 1 for hits... unspecified; pass NULL too).
  * Any of rows_out, hit_out, ones_list_dev, n_ones_dev, cmask_dev may be NULL.
- * 1 <= n <= FFC_LRU_MAX_BATCH.  n_ones_dev is accumulated (caller zeroes it). */
+ * 1 <= n <= FFC_LRU_MAX_BATCH.  n_ones_dev is accumulated (caller zeroes it).
+ * n_dev (optional device scalar) / n_base: when the number of keys is only known on the device (a rank's
+ * share of an all-gathered batch), the call processes keys [0, clamp(*n_dev - n_base, 0, n)) and leaves the
+ * outputs of the remaining positions untouched; pass NULL, 0 otherwise. */
 int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int journal, uint8_t* qpos_dev,
                    int32_t* rows_out, int32_t* cols_out, uint8_t* hit_out, int32_t* ones_list_dev,
-                   int32_t* n_ones_dev, uint32_t* cmask_dev, void* stream);
+                   int32_t* n_ones_dev, uint32_t* cmask_dev, const int32_t* n_dev, int n_base, void* stream);
 
 /* lru.py:147-151 view() / lru.py:145-146 __contains__ for n keys: slot or -1, recency untouched
  * (ffc.py:189-194 / 242-246 probe labels).  Any n >= 1. */
 int ffc_lru_view(ffc_lru_t* h, const int64_t* keys_dev, int n, int32_t* slots_out, void* stream);
 
 /* lru.py:252-255 rollback_steps(steps): undo the newest `steps` journaled accesses (clamped to the
- * journal length, like the reference) including their qpos changes (ffc.py:256-257). */
+ * journal length, like the reference) including their qpos changes (ffc.py:256-257); steps < 0 undoes
+ * everything outstanding. */
 int ffc_lru_undo(ffc_lru_t* h, int64_t steps, uint8_t* qpos_dev, void* stream);
 
 /* Bounded maintenance between passes (ring compaction, hash-table rebuild) when the host-side
@@ -100,7 +104,7 @@ int ffc_lru_import(ffc_lru_t* h, const int64_t* keys_host, const int32_t* slots_
  * Prototype queue scatter (replaces ffc.py:179-182, 237-241, 255).
  * queue_f32_dev: [2, Q, D] fp32 (the reference's `queue` buffer, checkpoint contract 'fc').
  * queue_bf16_dev: [2, Q, D] bf16 mirror read by the tensor-core sweep (may be NULL).
- * For each i: queue[rows[i], cols[i], :] = g[i, :]; a repeated (row, col) pair resolves to the LAST
+ * For each i with cols[i] >= 0: queue[rows[i], cols[i], :] = g[i, :]; a repeated (row, col) pair resolves to the LAST
  * occurrence (the reference's serial CPU behaviour; undefined on its CUDA path).
  * undo_f32_dev ([B, D] fp32, may be NULL): receives the previous fp32 row of every winning write so
  * that ffc_queue_restore can put it back (ffc.py:240 `old_tensor`, ffc.py:255).

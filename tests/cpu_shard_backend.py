@@ -1,0 +1,184 @@
+"""TEST-ONLY torch/CPU stand-in for one rank's shard of the sharded FFC head (ffc_b200.dist.CudaShardBackend).
+
+It restates, in fp64 torch, what the CUDA kernels compute per shard -- bookkeeping through the oracle LRU, the sweep
+statistics (softmax denominators relative to the fixed max M = scale, sum_j p~_j W_j, target cosines, top-k
+candidates) and the finalize formulas of csrc/head.cu -- so that the collective choreography of ffc_b200.dist can be
+run on CPU under gloo.  It is never imported by the product.
+"""
+import math
+
+import torch
+
+from oracle.lru_ref import LRU
+
+
+class _LruShim:
+    def __init__(self, cap):
+        self.ref = LRU(cap)
+
+    def restore_arrays(self, keys, slots):
+        self.ref.restore(list(zip(keys.tolist(), slots.tolist())))
+
+    def state_dict(self):
+        return self.ref.state_dict()
+
+
+class CpuShardBackend:
+    dtype = torch.float64
+
+    def __init__(self, feat_dim, q_local, q_total, col_offset, max_rows, scale, loss_type, margin, topk, queue=None):
+        self.D, self.Ql, self.off, self.k = feat_dim, q_local, col_offset, topk
+        self.scale, self.loss_type, self.margin = scale, loss_type, margin
+        self.lru = _LruShim(q_local)
+        self.qpos = [0] * q_local
+        self.queue = torch.zeros(2, q_local, feat_dim, dtype=torch.float64) if queue is None else queue.double().clone()
+        self.ones = []
+
+    def new_stats(self, n, n_ranks):
+        return dict(red=torch.zeros(8, n, dtype=torch.float64), osum=torch.zeros(4, n, self.D, dtype=torch.float64),
+                    topv=torch.full((n_ranks, 3, n, self.k), -math.inf, dtype=torch.float64),
+                    topi=torch.full((n_ranks, 3, n, self.k), -1, dtype=torch.int32))
+
+    # ffc.py:162-177 / 214-235 over the shard's own keys
+    def assign(self, keys_compact, n_dev, journal):
+        n = int(n_dev.item())
+        ref = self.lru.ref
+        self.rows, self.cols, self.ones, self.saved = [], [], [], {}
+        for k in keys_compact[:n].tolist():
+            known = k in ref
+            s = ref.try_get(k) if journal else ref.get(k)
+            if journal and s not in self.saved:
+                self.saved[s] = self.qpos[s]
+            if known:
+                self.rows.append(self.qpos[s])
+                if s not in self.ones:
+                    self.ones.append(s)
+                self.qpos[s] ^= 1
+            else:
+                self.rows.append(0)
+                self.qpos[s] = 1
+            self.cols.append(s)
+        self.journal = journal
+
+    def scatter(self, g_compact, save_undo):
+        last = {}
+        for i, rc in enumerate(zip(self.rows, self.cols)):
+            last[rc] = i
+        self.undo = {rc: self.queue[rc[0], rc[1]].clone() for rc in last} if save_undo else None
+        for rc, i in last.items():
+            self.queue[rc[0], rc[1]] = g_compact[i].double()
+
+    def restore(self):
+        for rc, v in self.undo.items():
+            self.queue[rc[0], rc[1]] = v
+        for s, v in self.saved.items():
+            self.qpos[s] = v
+        self.lru.ref.rollback_steps(len(self.cols))
+
+    def view(self, keys):
+        return torch.tensor([self.lru.ref.view(k) for k in keys.tolist()], dtype=torch.int32)
+
+    def _row_info(self, label):
+        tcol = torch.where((label >= self.off) & (label < self.off + self.Ql), label - self.off, torch.full_like(label, -1)).long()
+        pos = {s: j for j, s in enumerate(self.ones)}
+        tpos = torch.tensor([pos.get(int(t), -1) for t in tcol.tolist()], dtype=torch.long)
+        return tcol, tpos
+
+    def sweep(self, p_all, label, st, slot):
+        p = p_all.double()
+        n, k, s, M = p.shape[0], self.k, self.scale, self.scale
+        tcol, tpos = self._row_info(label)
+        out = label < 0
+        W0, W1 = self.queue[0], self.queue[1]
+        ones = torch.tensor(self.ones, dtype=torch.long)
+        red, osum = st['red'], st['osum']
+        cos = p @ W0.t()
+        excl = torch.zeros(n, self.Ql, dtype=torch.bool)
+        excl[:, ones] = True
+        ar = torch.arange(n)
+        has_t = tcol >= 0
+        excl[ar[has_t], tcol[has_t]] = True
+        pt = torch.exp(s * cos - M).masked_fill(excl, 0.0)
+        red[0] = red[1] = pt.sum(1)
+        osum[0] = osum[1] = pt @ W0
+        st['topv'][slot].fill_(-math.inf)
+        st['topi'][slot].fill_(-1)
+
+        def put_topk(vals, idx_map, excl_mask, dst):
+            v = vals.masked_fill(excl_mask, -math.inf)
+            kk = min(k, v.shape[1])
+            if kk == 0:
+                return
+            tv, ti = torch.topk(v, kk, dim=1)
+            gi = idx_map[ti].to(torch.int32)
+            gi = torch.where(torch.isinf(tv), torch.full_like(gi, -1), gi)
+            st['topv'][slot, dst, out, :kk] = tv[out]
+            st['topi'][slot, dst, out, :kk] = gi[out]
+
+        cmask_only = torch.zeros(n, self.Ql, dtype=torch.bool)
+        cmask_only[:, ones] = True
+        put_topk(cos, self.off + torch.arange(self.Ql), cmask_only, 0)
+        for l, W in enumerate((W0, W1)):
+            Ws = W[ones]
+            cs = p @ Ws.t()
+            ex = torch.zeros(n, len(self.ones), dtype=torch.bool)
+            has_p = tpos >= 0
+            ex[ar[has_p], tpos[has_p]] = True
+            ps = torch.exp(s * cs - M).masked_fill(ex, 0.0)
+            red[2 + l] = ps.sum(1)
+            osum[2 + l] = ps @ Ws
+            put_topk(cs, self.off + ones, torch.zeros_like(ex), 1 + l)
+        t0 = torch.zeros(n, dtype=torch.float64)
+        t1 = torch.zeros(n, dtype=torch.float64)
+        rows = ar[has_t]
+        t0[rows] = (p[rows] * W0[tcol[rows]]).sum(1)
+        wt = torch.where((tpos[rows] >= 0).unsqueeze(1), W1[tcol[rows]], W0[tcol[rows]])
+        t1[rows] = (p[rows] * wt).sum(1)
+        red[4], red[5], red[6], red[7] = t0, t1, has_t.double(), torch.zeros(n, dtype=torch.float64)
+
+    def finalize(self, p_all, label, st, n_ranks):
+        n, D, k, s, M, m = p_all.shape[0], self.D, self.k, self.scale, self.scale, self.margin
+        tcol, tpos = self._row_info(label)
+        out = label < 0
+        n_pos, n_out = int((~out).sum()), int(out.sum())
+        red, osum = st['red'], st['osum']
+        W = self.queue
+        loss = torch.zeros((), dtype=torch.float64)
+        dp = torch.zeros(n, D, dtype=torch.float64)
+        for i in range(n):
+            if not out[i]:
+                for l in range(2):
+                    ct = float(red[4 + l, i])
+                    if self.loss_type == 'AM':
+                        ft, dft = ct - m, 1.0
+                    else:
+                        sn = math.sqrt(1.0 - ct * ct)
+                        ft, dft = ct * math.cos(m) - sn * math.sin(m), math.cos(m) + ct * math.sin(m) / sn
+                    zt = s * ft
+                    et = math.exp(zt - M)
+                    L = float(red[l, i] + red[2 + l, i]) + et
+                    loss += (math.log(L) + M - zt) / n_pos
+                    dp[i] += (s / L / n_pos) * (osum[l, i] + osum[2 + l, i])
+                    if tcol[i] >= 0:
+                        row = 1 if (l == 1 and tpos[i] >= 0) else 0
+                        dp[i] += (s * (et / L - 1.0) * dft / n_pos) * W[row, tcol[i]]
+            else:
+                wneg = 1.0 / (n_out * k)
+                for l in range(2):
+                    cand = []
+                    for r in range(n_ranks):
+                        for src, setid in ((0, 0), (1, 1 + l)):
+                            for q in range(k):
+                                v, gi = float(st['topv'][r, setid, i, q]), int(st['topi'][r, setid, i, q])
+                                if gi >= 0:
+                                    cand.append((v, gi, src))
+                    cand.sort(key=lambda t: -t[0])
+                    for v, gi, src in cand[:k]:
+                        loss += max(v, 0.0) * wneg
+                        loc = gi - self.off
+                        if v >= 0 and 0 <= loc < self.Ql:
+                            dp[i] += wneg * W[l if src else 0, loc]
+        return loss.reshape(()), dp
+
+    def end_pass(self):
+        pass

@@ -1,0 +1,115 @@
+"""world_size-2 gloo test (CPU) of the sharded head's collective choreography (ffc_b200/dist.py).
+
+The per-shard compute is the torch stand-in of tests/cpu_shard_backend.py; the expectation is the dense oracle run
+on the concatenated global batch with the sharded bookkeeping (one reference LRU(Q/R) per rank, keys routed by
+id mod R, global slot = rank*Q/R + local slot)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from oracle.head_ref import HeadOracle, add_margin, hard_neg_k
+from oracle.lru_ref import LRU
+
+
+class ShardedOracle(HeadOracle):
+    """HeadOracle whose LRU / queue positions are partitioned like ffc_b200.dist."""
+
+    def __init__(self, R, *a, **k):
+        super().__init__(*a, **k)
+        self.R, self.Ql = R, self.Q // R
+        self.lrus = [LRU(self.Ql) for _ in range(R)]
+        self.lru = self
+
+    # the subset of the LRU surface HeadOracle uses, routed by identity
+    def _route(self, key):
+        r = key % self.R
+        return r, self.lrus[r]
+
+    def __contains__(self, key):
+        return key in self._route(key)[1]
+
+    def get(self, key):
+        r, l = self._route(key)
+        return r * self.Ql + l.get(key)
+
+    def try_get(self, key):
+        r, l = self._route(key)
+        self._log.append(r)
+        return r * self.Ql + l.try_get(key)
+
+    def view(self, key):
+        r, l = self._route(key)
+        v = l.view(key)
+        return v if v < 0 else r * self.Ql + v
+
+    def rollback_steps(self, n):
+        for r in reversed(self._log[-n:]):
+            self.lrus[r].rollback_one_step()
+        del self._log[-n:]
+
+    def head_pass(self, *a, **k):
+        if not hasattr(self, '_log'):
+            self._log = []
+        return super().head_pass(*a, **k)
+
+
+def _worker(rank, world, port, loss_type, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from cpu_shard_backend import CpuShardBackend
+        from ffc_b200.dist import ShardedFFCHead
+        torch.manual_seed(0)
+        D, Q, B, n_ids, steps = 16, 64, 12, 90, 4
+        margin = 0.5 if loss_type == 'Arc' else 0.4
+        q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64), dim=2)
+        Ql = Q // world
+        head = ShardedFFCHead(D, Q, 32.0, loss_type, margin, max_batch=B,
+                              backend_factory=lambda ql, off, n: CpuShardBackend(D, ql, Q, off, n, 32.0, loss_type, margin, hard_neg_k(Q),
+                                                                                 queue=q0[:, off:off + ql]))
+        oracle = ShardedOracle(world, D, Q, 32.0, loss_type, margin, queue=q0, dtype=torch.float64)
+        gen = torch.Generator().manual_seed(5)
+        cen = F.normalize(torch.randn(n_ids, D, generator=gen, dtype=torch.float64))
+        for s in range(steps):
+            # the same global batch on every rank; each rank feeds its own slice
+            xl = torch.randint(0, n_ids, (world * B,), generator=gen)
+            yl = torch.cat([xl[:world * B // 2], torch.randint(0, n_ids, (world * B - world * B // 2,), generator=gen)])
+            x = F.normalize(cen[xl] + 0.4 * torch.randn(world * B, D, generator=gen, dtype=torch.float64))
+            y = F.normalize(cen[yl] + 0.4 * torch.randn(world * B, D, generator=gen, dtype=torch.float64))
+            sl = slice(rank * B, (rank + 1) * B)
+            xs = x[sl].clone().requires_grad_(True)
+            ys = y[sl].clone().requires_grad_(True)
+            loss = head.forward(xs, ys, xl[sl], yl[sl])
+            loss.backward()
+            xo = x.clone().requires_grad_(True)
+            yo = y.clone().requires_grad_(True)
+            ref = oracle.forward(xo, yo, xl.tolist(), yl.tolist())
+            ref.backward()
+            assert abs(float(loss) - float(ref)) <= 1e-9 * abs(float(ref)), (s, float(loss), float(ref))
+            assert torch.allclose(xs.grad, xo.grad[sl], rtol=1e-8, atol=1e-12), s
+            assert torch.allclose(ys.grad, yo.grad[sl], rtol=1e-8, atol=1e-12), s
+            # per-shard LRU == reference LRU(Q/R) fed the keys it owns
+            assert head.backend.lru.state_dict() == oracle.lrus[rank].state_dict()
+            # labels agree with the oracle's global slots
+            assert head._last['label'].tolist() == oracle.trace[-1]['labels']
+        ret[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('loss_type', ['AM', 'Arc'])
+def test_sharded_head_world2_gloo(loss_type):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, loss_type, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: 'ok', 1: 'ok'}

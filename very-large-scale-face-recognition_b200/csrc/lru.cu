@@ -209,6 +209,8 @@ struct ResolveArgs {
   const int64_t* keys;
   const int32_t* s0;
   int n;
+  const int32_t* n_dev;   // optional device-side key count (sharded callers): n_eff = clamp(*n_dev - n_base, 0, n)
+  int n_base;
   int do_journal;
   uint8_t* qpos;
   int32_t* rows_out;
@@ -393,11 +395,19 @@ __device__ void run_sim(ResolveSmem& S, const ResolveArgs& a, int64_t head, int 
   S.sim_done = (i >= a.n);
 }
 
-__global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a) {
+__global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_in) {
+  ResolveArgs a = a_in;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResolveSmem& S = *reinterpret_cast<ResolveSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = a.n;
+  int n_eff = a.n;
+  if (a.n_dev) {
+    n_eff = *a.n_dev - a.n_base;
+    n_eff = n_eff < 0 ? 0 : (n_eff > a.n ? a.n : n_eff);
+  }
+  const int n = n_eff;
+  if (n == 0) return;
+  a.n = n;
   LruState* st = a.st;
   const int cur0 = st->cur_idx;
   const int64_t head = st->head, tail = st->tail, jlen = st->jlen;
@@ -857,7 +867,7 @@ extern "C" int ffc_lru_view(ffc_lru_t* h, const int64_t* keys_dev, int n, int32_
 
 extern "C" int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int journal, uint8_t* qpos_dev, int32_t* rows_out,
                               int32_t* cols_out, uint8_t* hit_out, int32_t* ones_list_dev, int32_t* n_ones_dev, uint32_t* cmask_dev,
-                              void* stream) {
+                              const int32_t* n_dev, int n_base, void* stream) {
   FFC_REQUIRE(h && keys_dev && cols_out, "ffc_lru_assign: NULL argument");
   FFC_REQUIRE(n >= 1 && n <= NB, "ffc_lru_assign: n=%d outside [1,%d]", n, NB);
   FFC_REQUIRE(!ones_list_dev || (n_ones_dev && cmask_dev), "ffc_lru_assign: ones_list needs n_ones and cmask");
@@ -886,6 +896,8 @@ extern "C" int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int 
   a.keys = keys_dev;
   a.s0 = h->s0;
   a.n = n;
+  a.n_dev = n_dev;
+  a.n_base = n_base;
   a.do_journal = journal ? 1 : 0;
   a.qpos = qpos_dev;
   a.rows_out = rows_out;
@@ -903,8 +915,9 @@ extern "C" int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int 
 }
 
 extern "C" int ffc_lru_undo(ffc_lru_t* h, int64_t steps, uint8_t* qpos_dev, void* stream) {
-  FFC_REQUIRE(h != nullptr && steps >= 0, "ffc_lru_undo: bad arguments");
+  FFC_REQUIRE(h != nullptr, "ffc_lru_undo: NULL handle");
   cudaStream_t s = (cudaStream_t)stream;
+  if (steps < 0) steps = h->jlen_host;   // everything outstanding (the device-side journal length decides)
   const int64_t m = std::min<int64_t>(steps, h->jlen_host);
   if (m == 0) return FFC_OK;
   lru_undo_kernel<<<1, NT, sizeof(UndoSmem), s>>>(h->ht_key, h->ht_slot, h->T / 32, h->slot_key, h->last_pos, h->st, h->journal, m, qpos_dev);

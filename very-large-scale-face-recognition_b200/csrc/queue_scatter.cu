@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ 
                                                             const int32_t* __restrict__ cols, const float* __restrict__ g, int B, int64_t Q, int D,
                                                             float* __restrict__ undo) {
   const int i = blockIdx.x;
+  if (cols[i] < 0) return;   // padded position (sharded callers)
   if (later_duplicate(rows, cols, i, B)) return;
   const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
   const float4* src = reinterpret_cast<const float4*>(g + (int64_t)i * D);
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ 
 __global__ void __launch_bounds__(128) queue_restore_kernel(float* __restrict__ qf, __nv_bfloat16* __restrict__ qh, const int32_t* __restrict__ rows,
                                                             const int32_t* __restrict__ cols, const float* __restrict__ undo, int B, int64_t Q, int D) {
   const int i = blockIdx.x;
+  if (cols[i] < 0) return;
   if (later_duplicate(rows, cols, i, B)) return;
   const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
   const float4* src = reinterpret_cast<const float4*>(undo + (int64_t)i * D);

@@ -40,7 +40,7 @@ PROTOTYPES = {
     'ffc_lru_destroy': (c_int, [c_void_p]),
     'ffc_lru_clear': (c_int, [c_void_p, c_void_p]),
     'ffc_lru_assign': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'ffc_lru_view': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'ffc_lru_undo': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'ffc_lru_maintain': (c_int, [c_void_p, c_void_p]),

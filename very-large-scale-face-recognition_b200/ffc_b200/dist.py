@@ -1,0 +1,255 @@
+"""Column-sharded FFC head over the GPUs of one node (partial-FC style; nothing like it exists in the reference,
+which is single-process -- SURVEY.md section 8(e)).
+
+Partition: rank r of R owns queue slots [r*Q/R, (r+1)*Q/R) -- fp32 rows, bf16 mirror, queue positions -- and the
+LRU of the identities with ``id mod R == r`` (an exact, balanced "identity hash" for dense class indices).  A rank's
+LRU is bit-exact with the reference ``LRU(Q/R)`` fed the keys it owns in global batch order (rank-major, then row).
+
+One head pass (embeddings in) per rank:
+  all-gather p, g, probe/gallery labels            (NCCL over NVLink)
+  own gallery keys  -> device LRU assign + enqueue scatter into the local shard      (ffc.py:162-182 / 214-241)
+  probe labels      -> local view, global slot = r*Q/R + local, all-reduce MAX       (ffc.py:189-194)
+  sweep of the local shard for ALL R*B rows        (same tcgen05 kernel as on one GPU)
+  all-reduce SUM of the per-row softmax denominators / target cosines, all-gather of the top-k candidates
+  finalize -> loss (identical on every rank) and this rank's partial dLoss/dp for all rows
+  reduce-scatter SUM -> dLoss/dp of the rank's own B rows
+No collective touches the B x Q logits (they never exist); the exchanged bytes are O(R*B*D).
+
+The per-rank compute sits behind a small backend interface so that the collective choreography can be exercised on
+CPU (gloo, world_size 2) by the tests with a torch stand-in; the product backend is :class:`CudaShardBackend`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from ._capi import HeadConfig, HeadPass, HeadStats, check
+from .ffc import hard_neg_k
+from .lru import LRU
+
+
+class CudaShardBackend:
+    """One rank's shard on the device, through the C ABI (no fallback)."""
+
+    def __init__(self, feat_dim, q_local, q_total, col_offset, max_rows, scale, loss_type, margin, topk, precision, device):
+        if not torch.cuda.is_available():
+            raise _capi.FFCError('the sharded FFC head needs CUDA devices (no CPU fallback)')
+        self.lib = _capi.lib()
+        self.dev = torch.device(device)
+        self.D, self.Ql, self.Q, self.off, self.R_rows, self.k = feat_dim, q_local, q_total, col_offset, max_rows, topk
+        dev, D, Ql, n = self.dev, feat_dim, q_local, max_rows
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self.lru = LRU(Ql, device=dev)
+            q = torch.rand(2, Ql, D, device=dev)
+            q /= q.norm(dim=2, keepdim=True).clamp_min(1e-12)
+            self.queue = q
+            self.queue_bf16 = torch.empty(2, Ql, D, dtype=torch.bfloat16, device=dev)
+            self.qpos = torch.zeros(Ql, dtype=torch.uint8, device=dev)
+            self.cmask = torch.zeros((Ql + 31) // 32 + 8, **i32)
+            self.rows = torch.zeros(n, **i32)
+            self.cols = torch.full((n,), -1, **i32)
+            self.ones_list = torch.empty(n, **i32)
+            self.n_ones = torch.zeros(1, **i32)
+            self.undo_rows = torch.empty(n, D, **f32)
+            self.loss_buf = torch.zeros(1, **f32)
+            cfg = HeadConfig(n, Ql, q_total, col_offset, D, _capi.LOSS_TYPES[loss_type], scale, margin, topk, _capi.PRECISIONS[precision])
+            h = C.c_void_p()
+            check(self.lib.ffc_head_create(C.byref(cfg), C.byref(h)))
+            self._h = h
+        self.sync_mirror()
+
+    def __del__(self):
+        h = self.__dict__.pop('_h', None)
+        if h:
+            try:
+                self.lib.ffc_head_destroy(h)
+            except Exception:
+                pass
+
+    def _s(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def sync_mirror(self):
+        check(self.lib.ffc_cast_bf16(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.queue.numel(), self._s()))
+
+    def set_queue(self, q):
+        self.queue.copy_(q.to(self.dev))
+        self.sync_mirror()
+
+    def new_stats(self, n, n_ranks):
+        dev, D, k = self.dev, self.D, self.k
+        red = torch.zeros(8, n, dtype=torch.float32, device=dev)          # rows 0-3 lsum, 4-7 tgt: one all-reduce
+        return dict(red=red, osum=torch.empty(4, n, D, dtype=torch.float32, device=dev),
+                    topv=torch.empty(n_ranks, 3, n, k, dtype=torch.float32, device=dev),
+                    topi=torch.empty(n_ranks, 3, n, k, dtype=torch.int32, device=dev))
+
+    # -- pass steps -------------------------------------------------------------------------------
+    def assign(self, keys_compact, n_dev, journal):
+        n = keys_compact.numel()
+        self.n_ones.zero_()
+        self.cols[:n].fill_(-1)
+        self.lru.assign(keys_compact, journal=journal, qpos=self.qpos, rows=self.rows, cols=self.cols, ones_list=self.ones_list,
+                        n_ones=self.n_ones, cmask=self.cmask, n_dev=n_dev)
+        self._n = n
+
+    def scatter(self, g_compact, save_undo):
+        check(self.lib.ffc_queue_scatter(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                         g_compact.data_ptr(), self._n, self.Ql, self.D, self.undo_rows.data_ptr() if save_undo else None, self._s()))
+
+    def restore(self):
+        check(self.lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                         self.undo_rows.data_ptr(), self._n, self.Ql, self.D, self._s()))
+        self.lru.undo(-1, self.qpos)
+
+    def view(self, keys):
+        return self.lru.view_batch(keys)
+
+    def _structs(self, p_all, label, st, slot):
+        n = p_all.shape[0]
+        hp = HeadPass(p_all.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), label.data_ptr(), self.ones_list.data_ptr(),
+                      self.n_ones.data_ptr(), self.cmask.data_ptr(), n)
+        red = st['red']
+        hs = HeadStats(red.data_ptr(), st['osum'].data_ptr(), red.data_ptr() + 4 * n * 4, st['topv'][slot].data_ptr(), st['topi'][slot].data_ptr())
+        return hp, hs
+
+    def sweep(self, p_all, label, st, rank_slot):
+        hp, hs = self._structs(p_all, label, st, rank_slot)
+        check(self.lib.ffc_head_sweep(self._h, C.byref(hp), C.byref(hs), self._s()))
+
+    def finalize(self, p_all, label, st, n_ranks):
+        hp, hs = self._structs(p_all, label, st, 0)
+        self.loss_buf.zero_()
+        dp = torch.empty(p_all.shape[0], self.D, dtype=torch.float32, device=self.dev)
+        check(self.lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), n_ranks, self.loss_buf.data_ptr(), dp.data_ptr(), self._s()))
+        return self.loss_buf[0].clone(), dp
+
+    def end_pass(self):
+        self.cmask.zero_()
+
+    def set_timing(self, enable):
+        check(self.lib.ffc_head_set_timing(self._h, 1 if enable else 0))
+
+    def get_timing(self):
+        ms, n = C.c_double(), C.c_int64()
+        check(self.lib.ffc_head_get_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+class _ShardedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, head, g, probe_label, gallery_label, commit):
+        loss, dp = head.head_pass(p.detach(), g, probe_label, gallery_label, commit)
+        ctx.save_for_backward(dp)
+        ctx.p_dtype = p.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dp,) = ctx.saved_tensors
+        return (dp * grad_out).to(ctx.p_dtype), None, None, None, None, None
+
+
+class ShardedFFCHead:
+    """R-way column-sharded head.  ``backend_factory(q_local, col_offset, max_rows) -> backend`` is for the CPU tests."""
+
+    def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024, device=None,
+                 group=None, backend_factory=None):
+        assert dist.is_initialized(), 'torch.distributed must be initialised (one process per GPU)'
+        assert loss_type in ('AM', 'Arc'), 'the sharded head supports AM / Arc (SV needs the target cosine before the sweep)'
+        self.group = group
+        self.R = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        assert queue_size % self.R == 0, 'queue_size must be divisible by the number of ranks'
+        self.D, self.Q, self.Ql = feat_dim, queue_size, queue_size // self.R
+        self.B = max_batch
+        self.k = hard_neg_k(queue_size)
+        self.off = self.rank * self.Ql
+        n = self.R * self.B
+        if backend_factory is None:
+            self.backend = CudaShardBackend(feat_dim, self.Ql, queue_size, self.off, n, scale, loss_type, margin, self.k, precision, device)
+            self.dev = torch.device(device)
+        else:
+            self.backend = backend_factory(self.Ql, self.off, n)
+            self.dev = torch.device('cpu')
+        self._nccl = dist.get_backend(group) == 'nccl'
+        self._stats = {}
+
+    # -- helpers ----------------------------------------------------------------------------------
+    def shard_of(self, keys):
+        """Owner rank of each identity: floor-mod (exact and balanced for dense class indices)."""
+        return torch.remainder(keys, self.R)
+
+    def _all_gather(self, t):
+        out = torch.empty((self.R * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def _reduce_scatter(self, t):
+        B = t.shape[0] // self.R
+        if self._nccl:
+            out = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.reduce_scatter_tensor(out, t, group=self.group)
+            return out
+        dist.all_reduce(t, group=self.group)                       # gloo (CPU tests): no reduce_scatter
+        return t[self.rank * B:(self.rank + 1) * B].clone()
+
+    def prefill_identity(self, n_ids):
+        """Steady state for benchmarks: identities 0..n_ids-1 resident, id i in local slot i // R of rank i % R."""
+        keys = torch.arange(self.rank, n_ids, self.R, dtype=torch.int64)[:self.Ql]
+        self.backend.lru.restore_arrays(keys, torch.arange(keys.numel(), dtype=torch.int32))
+
+    # -- one pass ---------------------------------------------------------------------------------
+    def head_pass(self, p, g, probe_label, gallery_label, commit):
+        be, R, dev = self.backend, self.R, self.dev
+        B = p.shape[0]
+        assert B == self.B, f'every rank must feed max_batch={self.B} rows (got {B})'
+        n = R * B
+        fdt = getattr(be, 'dtype', torch.float32)
+        p_all = self._all_gather(p.to(device=dev, dtype=fdt))
+        g_all = self._all_gather(g.detach().to(device=dev, dtype=fdt))
+        pl_all = self._all_gather(torch.as_tensor(probe_label).to(device=dev, dtype=torch.int64))
+        gl_all = self._all_gather(torch.as_tensor(gallery_label).to(device=dev, dtype=torch.int64))
+        # this rank's gallery keys, compacted in global batch order, without a host sync
+        mine = self.shard_of(gl_all) == self.rank
+        order = torch.argsort((~mine).to(torch.int8), stable=True)
+        n_mine = mine.sum().to(torch.int32).reshape(1)
+        be.assign(gl_all[order].contiguous(), n_mine, journal=not commit)
+        be.scatter(g_all[order].contiguous(), save_undo=not commit)
+        # probe labels: only the owner's LRU can know the key; everyone else answers -1
+        loc = be.view(pl_all)
+        label = torch.where(loc >= 0, loc + self.off, loc).to(torch.int32)
+        dist.all_reduce(label, op=dist.ReduceOp.MAX, group=self.group)
+        st = self._stats.get(n)
+        if st is None:
+            st = self._stats[n] = be.new_stats(n, R)
+        be.sweep(p_all, label, st, self.rank)
+        dist.all_reduce(st['red'], group=self.group)
+        if R > 1:
+            tv, ti = st['topv'][self.rank].clone(), st['topi'][self.rank].clone()
+            dist.all_gather_into_tensor(st['topv'].view(R * 3, n, -1), tv, group=self.group)
+            dist.all_gather_into_tensor(st['topi'].view(R * 3, n, -1), ti, group=self.group)
+        loss, dp_part = be.finalize(p_all, label, st, R)
+        dp = self._reduce_scatter(dp_part)
+        if not commit:
+            be.restore()
+        be.end_pass()
+        self._last = dict(label=label, n_mine=n_mine)
+        return loss, dp
+
+    def head(self, p, g, probe_label, gallery_label, commit=True):
+        return _ShardedFn.apply(p, self, g, probe_label, gallery_label, commit)
+
+    def forward(self, x, y, x_label, y_label):
+        """ffc.py:264-267 with embeddings in (rollback pass, then commit pass)."""
+        return self.head(x, y.detach(), x_label, y_label, commit=False) + self.head(y, x.detach(), y_label, x_label, commit=True)
+
+    def set_timing(self, enable):
+        self.backend.set_timing(enable)
+
+    def get_timing(self):
+        return self.backend.get_timing()

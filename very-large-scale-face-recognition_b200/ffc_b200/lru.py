@@ -41,7 +41,7 @@ class LRU:
     def _s(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def assign(self, keys, journal=False, qpos=None, rows=None, cols=None, hit=None, ones_list=None, n_ones=None, cmask=None):
+    def assign(self, keys, journal=False, qpos=None, rows=None, cols=None, hit=None, ones_list=None, n_ones=None, cmask=None, n_dev=None):
         """B sequential get() (journal=False) / try_get() (journal=True) calls; see ffc_lru_assign."""
         n = keys.numel()
         assert keys.dtype == torch.int64 and keys.is_cuda and keys.is_contiguous()
@@ -52,7 +52,7 @@ class LRU:
             m = min(_capi.LRU_MAX_BATCH, n - a)
             off = lambda t, sz: None if t is None else t.data_ptr() + a * sz
             check(self._lib.ffc_lru_assign(self._h, keys.data_ptr() + a * 8, m, 1 if journal else 0, ptr(qpos), off(rows, 4), off(cols, 4),
-                                           off(hit, 1), ptr(ones_list), ptr(n_ones), ptr(cmask), s))
+                                           off(hit, 1), ptr(ones_list), ptr(n_ones), ptr(cmask), ptr(n_dev), a, s))
         return cols
 
     def view_batch(self, keys, out=None):
