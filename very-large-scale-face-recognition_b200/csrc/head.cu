@@ -523,7 +523,7 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
   const int64_t R = cfg->max_rows, D = cfg->feat_dim;
-  h->part_rows_cap = std::max<int64_t>(R, 40960);
+  h->part_rows_cap = std::max<int64_t>(16 * R, 40960);
   h->max_chunks = 1024;
   FFC_CUDA(cudaMalloc(&h->p16, R * D * sizeof(__nv_bfloat16)));
   FFC_CUDA(cudaMalloc(&h->side_f32, 2 * R * D * sizeof(float)));

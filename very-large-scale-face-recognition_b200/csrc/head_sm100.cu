@@ -654,11 +654,25 @@ static int get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_
 
 int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
   (void)D;
-  const int row_tiles = (n_rows + BM - 1) / BM;
+  // items = row_tiles x chunks run as CTA pairs, 74 pairs at a time: pick the chunk count whose last wave is fullest
+  // (ties -> fewer chunks: fewer partials and fewer P loads / O write-outs)
+  const int row_tiles = std::max(1, (n_rows + BM - 1) / BM);
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(n_cols, BN));
-  int64_t chunks = 74 / std::max(row_tiles, 1);   // 74 CTA pairs on 148 SMs
-  chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
-  return (int)chunks;
+  const int max_c = (int)std::min<int64_t>(n_tiles, 40);
+  int best = 1;
+  double best_eff = 0.0;
+  for (int c = 1; c <= max_c; ++c) {
+    const int items = row_tiles * c;
+    const int waves = (items + 73) / 74;
+    // every item pays a fixed cost (prologue, P load, O write-out) worth about 12 tile-times
+    const double tiles_per_item = (double)n_tiles / c;
+    const double eff = ((double)items / (waves * 74.0)) * (tiles_per_item / (tiles_per_item + 12.0));
+    if (eff > best_eff * 1.005) {
+      best_eff = eff;
+      best = c;
+    }
+  }
+  return best;
 }
 
 static int ns2_for(int D) {

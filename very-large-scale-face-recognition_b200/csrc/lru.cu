@@ -482,21 +482,89 @@ __global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_
   if (tid == 0) S.n_nodes = n_distinct;
   __syncthreads();
 
-  // R2: initial candidates = number of evictions the batch needs if no resident entry is endangered
-  {
-    const int64_t fresh = a.cap - cur0;
-    int64_t need = (int64_t)n_miss0 - fresh;
-    if (need < 0) need = 0;
-    if (need > 0) fetch_candidates(S, a, head, (int)need);
-  }
-  // R3: sequential replay with on-demand refill
-  while (true) {
-    if (tid == 0) run_sim(S, a, head, cur0);
+  const int64_t fresh_room = a.cap - cur0;
+  if ((int64_t)n_miss0 <= fresh_room) {
+    // ---- fast path: no eviction can happen (all hits and/or fresh slots) => every position resolves independently:
+    // a key's j-th occurrence in the batch is a hit except a new key's first one; rows follow the qpos parity;
+    // the m-th new key (in batch order) takes slot cur_idx + m.  (lru.py:44-89 + ffc.py:166-177, closed form)
+    int* cnt = S.lh;              // [n_nodes] occurrences per node   (the smem hash is not needed any more)
+    int* lastp = S.lh + NB;       // [n_nodes] last position per node
     __syncthreads();
-    if (S.sim_done) break;
-    const int want = S.want;
-    fetch_candidates(S, a, head, want);
-    if (tid == 0 && S.n_untouched == 0 && S.scan_pos < head) S.err = 4;  // cannot happen
+    for (int c = tid; c < 2 * NB; c += NT) S.lh[c] = 0;
+    __syncthreads();
+    int nd = 0, occ = 0, prevpos = -1;
+    if (tid < n) {
+      nd = S.pnode[tid];
+      for (int j = 0; j < tid; ++j)
+        if (S.pnode[j] == nd) {
+          ++occ;
+          prevpos = j;
+        }
+      atomicAdd(&cnt[nd], 1);
+      atomicMax(&lastp[nd], tid);
+    }
+    const bool fresh_here = (tid < n) && occ == 0 && !(S.nflags[nd] & F_RES0);
+    int frank, ftotal;
+    cub::BlockScan<int, NT>(S.scan).ExclusiveSum(fresh_here ? 1 : 0, frank, ftotal);
+    if (fresh_here) S.nslot[nd] = cur0 + frank;
+    __syncthreads();
+    if (tid < n) {
+      const bool res0 = S.nflags[nd] & F_RES0;
+      const int32_t slot = S.nslot[nd];
+      uint8_t row, kind, oldq;
+      int64_t oldkey, oldpos;
+      if (res0) {
+        kind = K_HIT;
+        row = S.nqpos[nd] ^ (uint8_t)(occ & 1);
+        oldq = row;
+        oldkey = key;
+        oldpos = occ == 0 ? S.npos[nd] : head + prevpos;
+      } else if (occ == 0) {
+        kind = K_FRESH;
+        row = 0;
+        oldq = S.freshq[slot - cur0];
+        oldkey = KEY_EMPTY;
+        oldpos = -1;
+      } else {
+        kind = K_HIT;
+        row = 1 ^ (uint8_t)((occ - 1) & 1);
+        oldq = row;
+        oldkey = key;
+        oldpos = head + prevpos;
+      }
+      S.pcol[tid] = slot;
+      S.prow[tid] = row;
+      S.pkind[tid] = kind;
+      S.j_oldkey[tid] = oldkey;
+      S.j_oldpos[tid] = oldpos;
+      S.j_oldq[tid] = oldq;
+      S.j_cur[tid] = cur0 + frank;
+    }
+    __syncthreads();
+    if (tid < n && lastp[nd] == tid) {   // the last occurrence finalises the node
+      const bool res0 = S.nflags[nd] & F_RES0;
+      const int c = cnt[nd];
+      S.nqpos[nd] = res0 ? (S.nqpos[nd] ^ (uint8_t)(c & 1)) : (uint8_t)(1 ^ ((c - 1) & 1));
+      S.npos[nd] = head + tid;
+      S.nflags[nd] |= F_RES | F_TOUCHED;
+    }
+    if (tid == 0) S.cur = cur0 + ftotal;
+    __syncthreads();
+  } else {
+    // R2: initial candidates = number of evictions the batch needs if no resident entry is endangered
+    {
+      int64_t need = (int64_t)n_miss0 - fresh_room;
+      if (need > 0) fetch_candidates(S, a, head, (int)need);
+    }
+    // R3: sequential replay with on-demand refill
+    while (true) {
+      if (tid == 0) run_sim(S, a, head, cur0);
+      __syncthreads();
+      if (S.sim_done) break;
+      const int want = S.want;
+      fetch_candidates(S, a, head, want);
+      if (tid == 0 && S.n_untouched == 0 && S.scan_pos < head) S.err = 4;  // cannot happen
+    }
   }
   if (S.err) {
     if (tid == 0) st->err = S.err;
@@ -579,6 +647,7 @@ struct UndoSmem {
   JournalEntry e[NB];
   int32_t sh[LHSZ];      // slot hash: slot value or -1
   int32_t shmin[LHSZ];   // earliest entry index for that slot
+  int32_t shmut[LHSZ];   // 1 if any entry of that slot changed its key (fresh / evict)
 };
 
 __global__ void __launch_bounds__(NT, 1) lru_undo_kernel(int64_t* ht_key, int32_t* ht_slot, int64_t nwin, int64_t* slot_key,
@@ -596,6 +665,7 @@ __global__ void __launch_bounds__(NT, 1) lru_undo_kernel(int64_t* ht_key, int32_
     for (int c = tid; c < LHSZ; c += NT) {
       S.sh[c] = -1;
       S.shmin[c] = 0x7fffffff;
+      S.shmut[c] = 0;
     }
     if (tid < cnt) S.e[tid] = journal[a + tid];
     __syncthreads();
@@ -615,6 +685,7 @@ __global__ void __launch_bounds__(NT, 1) lru_undo_kernel(int64_t* ht_key, int32_
       }
       mycell = c;
       atomicMin(&S.shmin[c], tid);
+      if (S.e[tid].kind != K_HIT) S.shmut[c] = 1;
     }
     __syncthreads();
     // phase 1: remove every key this range inserted
@@ -633,7 +704,8 @@ __global__ void __launch_bounds__(NT, 1) lru_undo_kernel(int64_t* ht_key, int32_
       const JournalEntry& e = S.e[t];
       int c = (int)(mix64((uint64_t)e.slot) & (LHSZ - 1));
       while (S.sh[c] != e.slot) c = (c + 1) & (LHSZ - 1);
-      if (S.shmin[c] == t && e.kind != K_FRESH) ht_put_warp(ht_key, ht_slot, nwin, e.old_key, e.slot, lane);
+      // a slot that only saw hits still maps its key: nothing to repair in the table
+      if (S.shmin[c] == t && e.kind != K_FRESH && S.shmut[c]) ht_put_warp(ht_key, ht_slot, nwin, e.old_key, e.slot, lane);
     }
     __syncthreads();
     if (tid == 0) {
