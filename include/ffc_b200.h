@@ -160,7 +160,7 @@ typedef struct ffc_head_pass {
 /* Rank-local statistics produced by the sweep, consumed by finalize.  Layout (all fp32 unless
  * noted), n = n_rows, k = topk, D = feat_dim:
  *   lsum   [4][n]      softmax denominators (relative to the fixed max M = c*scale): common under loss 1,
- *                      common under loss 2 (differs only for SV), side0 (`ones` rows of queue[0]), side1 (queue[1])
+ *                      common under loss 2 (written and read only for SV), side0 (`ones` rows of queue[0]), side1 (queue[1])
  *   osum   [4][n][D]   sum_j p~_ij W_j for the same four column sets
  *   tgt    [4][n]      cos_t under queue[0], cos_t under W2, (owner flag as 1.0/0.0), spare
  *   topv   [3][n][k]   running top-k cosines (descending; -inf padded), topi int32 [3][n][k] GLOBAL slots

@@ -412,7 +412,8 @@ __global__ void __launch_bounds__(128) head_finalize_kernel(const FinalizeArgs a
         }
         const double zt = s * ft;
         const double et = exp(zt - M);
-        const double L = (double)a.lsum[l * n + i] + (double)a.lsum[(2 + l) * n + i] + et;
+        const int cs = a.loss_type == FFC_LOSS_SV ? l : 0;   // common-statistics slot
+        const double L = (double)a.lsum[cs * n + i] + (double)a.lsum[(2 + l) * n + i] + et;
         loss += (float)((log(L) + M - zt) / (double)n_pos);
         sh_coefO[l] = (float)(s / L / (double)n_pos);
         sh_coefT[l] = (float)(s * (et / L - 1.0) * dft / (double)n_pos);
@@ -459,8 +460,9 @@ __global__ void __launch_bounds__(128) head_finalize_kernel(const FinalizeArgs a
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float g = 0.f;
     if (!outl) {
-      g = sh_coefO[0] * (a.osum[((int64_t)0 * n + i) * D + d] + a.osum[((int64_t)2 * n + i) * D + d]) +
-          sh_coefO[1] * (a.osum[((int64_t)1 * n + i) * D + d] + a.osum[((int64_t)3 * n + i) * D + d]);
+      const float oc0 = a.osum[((int64_t)0 * n + i) * D + d];
+      const float oc1 = a.loss_type == FFC_LOSS_SV ? a.osum[((int64_t)1 * n + i) * D + d] : oc0;
+      g = sh_coefO[0] * (oc0 + a.osum[((int64_t)2 * n + i) * D + d]) + sh_coefO[1] * (oc1 + a.osum[((int64_t)3 * n + i) * D + d]);
       if (tc >= 0) g += sh_coefT[0] * w_elem(a, 0, tc, d) + sh_coefT[1] * w_elem(a, trow2, tc, d);
     } else {
       for (int e = 0; e < nw; ++e) {
@@ -658,10 +660,7 @@ extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   if (sv) {   // the SV hard-example threshold follows each loss's own target cosine (ffc.py:122)
     a.thr = h->thr + n;
     if ((rc = run_one_sweep(h, a, 0, 1, -1, out, c.col_offset, nullptr, s))) return rc;
-  } else {
-    FFC_CUDA(cudaMemcpyAsync(out->lsum + n, out->lsum, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    FFC_CUDA(cudaMemcpyAsync(out->osum + (int64_t)n * D, out->osum, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  }
+  }   // (AM / Arc: both losses share the common statistics; finalize reads slot 0 for both)
   // side sweeps over the gathered `ones` rows of queue[0] and queue[1]
   a.n_cols = c.max_rows;
   a.n_cols_dev = in->n_ones;

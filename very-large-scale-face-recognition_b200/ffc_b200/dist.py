@@ -178,6 +178,8 @@ class ShardedFFCHead:
             self.dev = torch.device('cpu')
         self._nccl = dist.get_backend(group) == 'nccl'
         self._stats = {}
+        import os
+        self._timing = [] if (os.environ.get('FFC_DIST_TIMING') and self._nccl) else None
 
     # -- helpers ----------------------------------------------------------------------------------
     def shard_of(self, keys):
@@ -204,40 +206,97 @@ class ShardedFFCHead:
         self.backend.lru.restore_arrays(keys, torch.arange(keys.numel(), dtype=torch.int32))
 
     # -- one pass ---------------------------------------------------------------------------------
-    def head_pass(self, p, g, probe_label, gallery_label, commit):
-        be, R, dev = self.backend, self.R, self.dev
-        B = p.shape[0]
-        assert B == self.B, f'every rank must feed max_batch={self.B} rows (got {B})'
-        n = R * B
+    def _mark(self, name):
+        # optional per-phase device timing (FFC_DIST_TIMING=1): CUDA events on the current stream, read by phase_times()
+        if self._timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._timing.append((name, ev))
+
+    def phase_times(self):
+        """{phase: total ms} accumulated since construction (synchronises); needs FFC_DIST_TIMING=1."""
+        out = {}
+        if self._timing:
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(self._timing[:-1], self._timing[1:]):
+                if n1 != 'start':
+                    out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def gather(self, emb, label):
+        """All-gather one side of the batch (embeddings [B,D] + labels [B]) -> ([R*B,D], int64 [R*B])."""
+        be, dev = self.backend, self.dev
+        assert emb.shape[0] == self.B, f'every rank must feed max_batch={self.B} rows (got {emb.shape[0]})'
         fdt = getattr(be, 'dtype', torch.float32)
-        p_all = self._all_gather(p.to(device=dev, dtype=fdt))
-        g_all = self._all_gather(g.detach().to(device=dev, dtype=fdt))
-        pl_all = self._all_gather(torch.as_tensor(probe_label).to(device=dev, dtype=torch.int64))
-        gl_all = self._all_gather(torch.as_tensor(gallery_label).to(device=dev, dtype=torch.int64))
+        e_all = self._all_gather(emb.detach().to(device=dev, dtype=fdt))
+        l_all = self._all_gather(torch.as_tensor(label).to(device=dev, dtype=torch.int64))
+        return e_all, l_all
+
+    def head_pass(self, p, g, probe_label, gallery_label, commit):
+        self._mark('start')
+        p_all, pl_all = self.gather(p, probe_label)
+        g_all, gl_all = self.gather(g, gallery_label)
+        self._mark('all_gather')
+        return self.head_pass_gathered(p_all, g_all, pl_all, gl_all, commit)
+
+    def forward_pair(self, x, y, x_label, y_label):
+        """ffc.py:264-267 on embeddings without autograd glue: both passes share ONE all-gather of (x, x_label) and
+        (y, y_label), since the commit pass only swaps the roles.  Returns (loss, dLoss/dx, dLoss/dy) for the rank's rows."""
+        self._mark('start')
+        x_all, xl_all = self.gather(x, x_label)
+        y_all, yl_all = self.gather(y, y_label)
+        self._mark('all_gather')
+        l2, dx = self.head_pass_gathered(x_all, y_all, xl_all, yl_all, False)
+        self._mark('start')
+        l1, dy = self.head_pass_gathered(y_all, x_all, yl_all, xl_all, True)
+        return l1 + l2, dx, dy
+
+    def head_pass_gathered(self, p_all, g_all, pl_all, gl_all, commit):
+        be, R, dev = self.backend, self.R, self.dev
+        n = p_all.shape[0]
         # this rank's gallery keys, compacted in global batch order, without a host sync
         mine = self.shard_of(gl_all) == self.rank
         order = torch.argsort((~mine).to(torch.int8), stable=True)
         n_mine = mine.sum().to(torch.int32).reshape(1)
-        be.assign(gl_all[order].contiguous(), n_mine, journal=not commit)
+        keys_c = gl_all[order].contiguous()
+        self._mark('route')
+        be.assign(keys_c, n_mine, journal=not commit)
+        self._mark('lru_assign')
         be.scatter(g_all[order].contiguous(), save_undo=not commit)
+        self._mark('scatter')
         # probe labels: only the owner's LRU can know the key; everyone else answers -1
         loc = be.view(pl_all)
         label = torch.where(loc >= 0, loc + self.off, loc).to(torch.int32)
         dist.all_reduce(label, op=dist.ReduceOp.MAX, group=self.group)
+        self._mark('labels')
         st = self._stats.get(n)
         if st is None:
             st = self._stats[n] = be.new_stats(n, R)
         be.sweep(p_all, label, st, self.rank)
+        self._mark('sweep')
         dist.all_reduce(st['red'], group=self.group)
-        if R > 1:
+        if R > 1 and st['topv'].dtype != torch.float32:     # CPU stand-in backend (fp64 values): two plain gathers
             tv, ti = st['topv'][self.rank].clone(), st['topi'][self.rank].clone()
             dist.all_gather_into_tensor(st['topv'].view(R * 3, n, -1), tv, group=self.group)
             dist.all_gather_into_tensor(st['topi'].view(R * 3, n, -1), ti, group=self.group)
+        elif R > 1:
+            # one all-gather for values and indices: both are 4-byte words
+            k = st['topv'].shape[-1]
+            mine_pack = torch.cat([st['topv'][self.rank].view(torch.int32), st['topi'][self.rank]], dim=0)    # [6, n, k]
+            pack = torch.empty(R * 6, n, k, dtype=torch.int32, device=mine_pack.device)
+            dist.all_gather_into_tensor(pack, mine_pack, group=self.group)
+            pack = pack.view(R, 2, 3, n, k)
+            st['topv'].copy_(pack[:, 0].view(torch.float32))
+            st['topi'].copy_(pack[:, 1])
+        self._mark('stat_exchange')
         loss, dp_part = be.finalize(p_all, label, st, R)
+        self._mark('finalize')
         dp = self._reduce_scatter(dp_part)
+        self._mark('reduce_scatter')
         if not commit:
             be.restore()
         be.end_pass()
+        self._mark('restore')
         self._last = dict(label=label, n_mine=n_mine)
         return loss, dp
 
