@@ -358,14 +358,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const float a2 = prm.a2, b2 = prm.b2;
       const int k = prm.k;
       float lsum = 0.f;
-      float tv[KMAX];
-      int32_t ti[KMAX];
+      // Hard-negative top-k (ffc.py:86-92) as a branch-free register list of integer keys: only POSITIVE cosines can
+      // contribute (clip(.., 0) zeroes the rest and their gradient), positive floats order like their int32 bit
+      // patterns, and the low 4 mantissa bits carry the column's index inside its 16-column chunk (value error 2^-19).
+      // tk[] descending keys (0 = empty), tc[] first column of the chunk the key came from.
+      int tk[KMAX], tc[KMAX];
 #pragma unroll
       for (int q = 0; q < KMAX; ++q) {
-        tv[q] = -INFINITY;
-        ti[q] = -1;
+        tk[q] = 0;
+        tc[q] = -1;
       }
-      float kth = -INFINITY;
+      int kth = 0;
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
       const uint32_t sw = (uint32_t)(r_local & 7);
@@ -382,6 +385,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
         const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
         const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
+        // A tile is "clean" for this warp when no column is excluded (no `ones` column, no row's target, not the
+        // ragged tail) and no row takes part in the top-k: then the chunk loop is pure ld -> ex2 -> pack -> st.async.
+        const bool clean = !warp_out && !__any_sync(0xffffffffu, (cm.x | cm.y | cm.z | cm.w) != 0u || (unsigned)(tcol - j0) < (unsigned)BN) &&
+                           (int64_t)j0 + BN <= n_cols;
+        if (clean) {
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t v[32];
+            tc_ld32(tmem_s + cc * 32, v);
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
+              float p0, p1, g0, g1;
+              if (SV) {
+                const bool m0 = x0 > thr, m1 = x1 > thr;
+                p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
+                p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
+                g0 = m0 ? p0 * SV_T : p0;
+                g1 = m1 ? p1 * SV_T : p1;
+              } else {
+                p0 = g0 = ex2f(fmaf(x0, a2, -b2));
+                p1 = g1 = ex2f(fmaf(x1, a2, -b2));
+              }
+              l0 += p0;
+              l1 += p1;
+              pk[c >> 1] = pack_bf16(g0, g1);
+            }
+            const uint32_t base = pt_remote + (uint32_t)((cc >> 1) * (BM * 128)) + (uint32_t)(r_local * 128);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t chunk16 = (uint32_t)((cc & 1) * 4 + q);
+              st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+          lsum += l0 + l1;
+        } else
 #pragma unroll 1
         for (int cc = 0; cc < BN / 16; ++cc) {
           uint32_t v[16];
@@ -396,21 +437,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             excl |= nv <= 0 ? 0xffffu : (0xffffu << nv) & 0xffffu;
           }
           const bool slow = __any_sync(0xffffffffu, excl != 0u);
-          // hard-negative top-k on the raw cosines of outlier rows
+          // hard-negative top-k on the raw cosines of outlier rows: all lanes run the same code; a lane with a
+          // candidate (key above its k-th) extracts its largest remaining key per round until no lane has any left
           if (warp_out) {
-            float mx = -INFINITY;
+            int key[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
-            if (outl && mx > kth) {
+            for (int c = 0; c < 16; ++c) {
+              key[c] = (int)((v[c] & 0xfffffff0u) | (uint32_t)c);
+              if (slow && ((excl >> c) & 1u)) key[c] = 0;
+            }
+            int bound = 0x7fffffff;      // keys >= bound were already extracted in this chunk
+            while (true) {
+              int mx = 0;
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float x = __uint_as_float(v[c]);
-                if (x > kth && !((excl >> c) & 1u)) {
-                  topk_insert<KMAX>(tv, ti, k, x, col0 + c);
+              for (int c = 0; c < 16; ++c) mx = max(mx, key[c] < bound ? key[c] : 0);
+              const bool has = outl && mx > kth;
+              if (!__any_sync(0xffffffffu, has)) break;
+              if (has) {
+                int xk = mx, xc = col0;
 #pragma unroll
-                  for (int q = 0; q < KMAX; ++q)
-                    if (q == k - 1) kth = tv[q];
+                for (int r = 0; r < KMAX; ++r) {
+                  if (r < k) {
+                    const bool pgt = xk > tk[r];
+                    const int nk = pgt ? xk : tk[r], nc = pgt ? xc : tc[r];
+                    xk = pgt ? tk[r] : xk;
+                    xc = pgt ? tc[r] : xc;
+                    tk[r] = nk;
+                    tc[r] = nc;
+                  }
                 }
+#pragma unroll
+                for (int r = 0; r < KMAX; ++r)
+                  if (r == k - 1) kth = tk[r];
+                bound = mx;
+              } else {
+                bound = 0;               // this lane is done with the chunk
               }
             }
           }
@@ -457,6 +518,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       // every MMA that read the W ring has completed once the last s_full was observed by its epilogue warpgroup;
       // synchronise the 8 epilogue warps (named barrier 1) before reusing the ring as staging
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      float tv[KMAX];
+      int32_t ti[KMAX];
+#pragma unroll
+      for (int q = 0; q < KMAX; ++q) {
+        const bool live = tk[q] > 0;
+        tv[q] = live ? __int_as_float(tk[q] & (int)0xfffffff0) : -INFINITY;
+        ti[q] = live ? tc[q] + (tk[q] & 15) : -1;
+      }
       if (g == 1) {
         stage_l[r_local] = lsum;
 #pragma unroll
@@ -469,14 +538,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       if (g == 0 && row_ok) {
         lsum += stage_l[r_local];
         if (outl) {
+          float kthv = -INFINITY;
 #pragma unroll
-          for (int q = 0; q < KMAX; ++q) {
+          for (int q = 0; q < KMAX; ++q)
+            if (q == k - 1) kthv = tv[q];
+#pragma unroll 1
+          for (int q = 0; q < k; ++q) {
             const float x = stage_v[r_local * KMAX + q];
-            if (q < k && x > kth) {
+            if (x > kthv) {
               topk_insert<KMAX>(tv, ti, k, x, stage_i[r_local * KMAX + q]);
 #pragma unroll
               for (int qq = 0; qq < KMAX; ++qq)
-                if (qq == k - 1) kth = tv[qq];
+                if (qq == k - 1) kthv = tv[qq];
             }
           }
         }
@@ -547,7 +620,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);   // frees P~ buffer pb: arrives in the S-CTA (cluster rank 0)
         }
         tc_commit(&bars.o_full);
+        mbar_wait(&bars.o_full, 0);     // one polling thread; the 8 epilogue warps block on a hardware barrier instead
       }
+      __syncwarp();
+      asm volatile("bar.sync 2, 288;" ::: "memory");
     } else if (warp >= 4) {
       // ---- O epilogue: TMEM -> global partial [chunk][row][D]; warpgroup g takes half of the columns ----
       const int g = (warp - 4) >> 2;
@@ -555,10 +631,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const int r_local = q4 * 32 + lane;
       const int row = row0 + r_local;
       const bool row_ok = row < prm.n_rows;
-      if (n_tiles > 0) {
-        mbar_wait_sleep(&bars.o_full, 0);
-        tc_fence_after();
-      }
+      asm volatile("bar.sync 2, 288;" ::: "memory");   // released by the MMA warp once every tcgen05.mma of the item has completed
+      tc_fence_after();
       const int half = D / 2;                      // D is a multiple of 64
       float* dst = prm.o_part + ((int64_t)chunk * prm.n_rows + (row_ok ? row : 0)) * D + g * half;
       for (int c0 = 0; c0 < half; c0 += 32) {
