@@ -33,7 +33,8 @@ constexpr int NS1 = 6;             // S-CTA W K-chunk stages (16 KB each)
 constexpr int NSB = 4;             // S accumulators in the S-CTA's TMEM (4 x 128 columns)
 constexpr int NPB = 3;             // P~ buffers in the O-CTA's shared memory
 constexpr int JB = 32;             // queue rows per O-CTA W stage
-constexpr int NTHREADS = 384;      // 12 warps
+constexpr int NEPI = 3;             // epilogue warpgroups in the S-CTA (tiles are dealt round-robin)
+constexpr int NTHREADS = 128 + NEPI * 128;   // 4 control warps + 12 epilogue warps
 constexpr int CHUNK1_BYTES = BN * KC * 2;   // 16384
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -56,8 +57,6 @@ struct Bars {   // all in the first 1024 bytes
   uint32_t pad;
 };
 static_assert(sizeof(Bars) <= 512, "barrier block too large");
-// staging for combining the two epilogue warpgroups lives at [512, 1024)? no: l/top-k go through registers + smem below
-constexpr int OFF_LSTAGE = 512;   // float[128] lsum of warpgroup 1
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -372,16 +371,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
       const uint32_t sw = (uint32_t)(r_local & 7);
-      for (int i = g; i < n_tiles; i += 2) {
+      // tile i uses S buffer i % NSB and P~ buffer i % NPB; NEPI == NPB, so this warpgroup always writes P~ buffer g
+      static_assert(NEPI == NPB, "epilogue warpgroups and P~ buffers are paired");
+      const int pb = g;
+      uint32_t pt_use = 0;
+      for (int i = g; i < n_tiles; i += NEPI, ++pt_use) {
         const int sb = i & (NSB - 1);
-        const int pb = i % NPB;
         const int j0 = (t_begin + i) * BN;
         // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
         uint4 cm = make_uint4(0u, 0u, 0u, 0u);
         if (prm.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(prm.cmask + (j0 >> 5)));
         mbar_wait(&bars.s_full[sb], (uint32_t)(i / NSB) & 1);
         tc_fence_after();
-        mbar_wait(&bars.pt_empty[pb], ((uint32_t)(i / NPB) & 1) ^ 1);
+        mbar_wait(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
         const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
         const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
         const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
@@ -512,12 +514,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
       }
       // ---- per-row partials: combine the two warpgroups through shared memory ----
-      float* stage_l = reinterpret_cast<float*>(smem + OFF_LSTAGE);               // [128]
-      float* stage_v = reinterpret_cast<float*>(sW1);                             // [128][KMAX] (W ring is idle now)
-      int32_t* stage_i = reinterpret_cast<int32_t*>(sW1 + BM * KMAX * 4);
+      float* stage_v = reinterpret_cast<float*>(sW1);                             // [2][128][KMAX] (W ring is idle now)
+      int32_t* stage_i = reinterpret_cast<int32_t*>(sW1 + 2 * BM * KMAX * 4);
+      float* stage_l = reinterpret_cast<float*>(sW1 + 4 * BM * KMAX * 4);         // [2][128]
       // every MMA that read the W ring has completed once the last s_full was observed by its epilogue warpgroup;
-      // synchronise the 8 epilogue warps (named barrier 1) before reusing the ring as staging
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // synchronise the 12 epilogue warps (named barrier 1) before reusing the ring as staging
+      asm volatile("bar.sync 1, 384;" ::: "memory");
       float tv[KMAX];
       int32_t ti[KMAX];
 #pragma unroll
@@ -526,30 +528,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         tv[q] = live ? __int_as_float(tk[q] & (int)0xfffffff0) : -INFINITY;
         ti[q] = live ? tc[q] + (tk[q] & 15) : -1;
       }
-      if (g == 1) {
-        stage_l[r_local] = lsum;
+      if (g >= 1) {
+        stage_l[(g - 1) * BM + r_local] = lsum;
 #pragma unroll
         for (int q = 0; q < KMAX; ++q) {
-          stage_v[r_local * KMAX + q] = tv[q];
-          stage_i[r_local * KMAX + q] = ti[q];
+          stage_v[((g - 1) * BM + r_local) * KMAX + q] = tv[q];
+          stage_i[((g - 1) * BM + r_local) * KMAX + q] = ti[q];
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 384;" ::: "memory");
       if (g == 0 && row_ok) {
-        lsum += stage_l[r_local];
-        if (outl) {
-          float kthv = -INFINITY;
+        float kthv = -INFINITY;
 #pragma unroll
-          for (int q = 0; q < KMAX; ++q)
-            if (q == k - 1) kthv = tv[q];
+        for (int q = 0; q < KMAX; ++q)
+          if (q == k - 1) kthv = tv[q];
 #pragma unroll 1
-          for (int q = 0; q < k; ++q) {
-            const float x = stage_v[r_local * KMAX + q];
-            if (x > kthv) {
-              topk_insert<KMAX>(tv, ti, k, x, stage_i[r_local * KMAX + q]);
+        for (int og = 0; og < NEPI - 1; ++og) {
+          lsum += stage_l[og * BM + r_local];
+          if (outl) {
+#pragma unroll 1
+            for (int q = 0; q < k; ++q) {
+              const float x = stage_v[(og * BM + r_local) * KMAX + q];
+              if (x > kthv) {
+                topk_insert<KMAX>(tv, ti, k, x, stage_i[(og * BM + r_local) * KMAX + q]);
 #pragma unroll
-              for (int qq = 0; qq < KMAX; ++qq)
-                if (qq == k - 1) kthv = tv[qq];
+                for (int qq = 0; qq < KMAX; ++qq)
+                  if (qq == k - 1) kthv = tv[qq];
+              }
             }
           }
         }
@@ -624,7 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       }
       __syncwarp();
       asm volatile("bar.sync 2, 288;" ::: "memory");
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
       // ---- O epilogue: TMEM -> global partial [chunk][row][D]; warpgroup g takes half of the columns ----
       const int g = (warp - 4) >> 2;
       const int q4 = warp & 3;
