@@ -68,12 +68,14 @@ class CpuShardBackend:
         for rc, i in last.items():
             self.queue[rc[0], rc[1]] = g_compact[i].double()
 
-    def restore(self):
-        for rc, v in self.undo.items():
-            self.queue[rc[0], rc[1]] = v
+    def undo_bookkeeping(self):
         for s, v in self.saved.items():
             self.qpos[s] = v
         self.lru.ref.rollback_steps(len(self.cols))
+
+    def restore_queue(self):
+        for rc, v in self.undo.items():
+            self.queue[rc[0], rc[1]] = v
 
     def view(self, keys):
         return torch.tensor([self.lru.ref.view(k) for k in keys.tolist()], dtype=torch.int32)

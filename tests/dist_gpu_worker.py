@@ -37,8 +37,12 @@ def main():
             sl = slice(rank * B, (rank + 1) * B)
             xs = x[sl].to(dev).requires_grad_(True)
             ys = y[sl].to(dev).requires_grad_(True)
-            loss = head.forward(xs, ys, xl[sl], yl[sl])
-            loss.backward()
+            if s == 2:      # the overlapped two-pass entry used by bench.py (commit bookkeeping under the rollback sweep)
+                loss, gx, gy = head.forward_pair(xs.detach(), ys.detach(), xl[sl], yl[sl])
+                xs.grad, ys.grad = gx, gy
+            else:
+                loss = head.forward(xs, ys, xl[sl], yl[sl])
+                loss.backward()
             xo, yo = x.double().requires_grad_(True), y.double().requires_grad_(True)
             ref = oracle.forward(xo, yo, xl.tolist(), yl.tolist())
             ref.backward()

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(128) head_gather_side_kernel(const float* __re
                                                                int max_rows, float* __restrict__ side_f32, __nv_bfloat16* __restrict__ side_bf16) {
   const int j = blockIdx.x;
   const int no = *n_ones_p;
+  if (j >= ((no + 127) & ~127)) return;   // only the tiles the side sweeps will touch need rows (zero padded to 128)
   const bool live = j < no;
   const int64_t slot = live ? ones_list[j] : 0;
   for (int r = 0; r < 2; ++r) {

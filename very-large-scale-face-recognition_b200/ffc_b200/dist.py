@@ -50,11 +50,10 @@ class CudaShardBackend:
             self.queue = q
             self.queue_bf16 = torch.empty(2, Ql, D, dtype=torch.bfloat16, device=dev)
             self.qpos = torch.zeros(Ql, dtype=torch.uint8, device=dev)
-            self.cmask = torch.zeros((Ql + 31) // 32 + 8, **i32)
-            self.rows = torch.zeros(n, **i32)
-            self.cols = torch.full((n,), -1, **i32)
-            self.ones_list = torch.empty(n, **i32)
-            self.n_ones = torch.zeros(1, **i32)
+            # per-pass bookkeeping state, two sets: the next pass's bookkeeping may overlap the current pass's sweep
+            self._sets = [dict(cmask=torch.zeros((Ql + 31) // 32 + 8, **i32), rows=torch.zeros(n, **i32), cols=torch.full((n,), -1, **i32),
+                               ones_list=torch.empty(n, **i32), n_ones=torch.zeros(1, **i32)) for _ in range(2)]
+            self.use_set(0)
             self.undo_rows = torch.empty(n, D, **f32)
             self.loss_buf = torch.zeros(1, **f32)
             cfg = HeadConfig(n, Ql, q_total, col_offset, D, _capi.LOSS_TYPES[loss_type], scale, margin, topk, _capi.PRECISIONS[precision])
@@ -73,6 +72,10 @@ class CudaShardBackend:
 
     def _s(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def use_set(self, i):
+        st = self._sets[i]
+        self.cmask, self.rows, self.cols, self.ones_list, self.n_ones = st['cmask'], st['rows'], st['cols'], st['ones_list'], st['n_ones']
 
     def sync_mirror(self):
         check(self.lib.ffc_cast_bf16(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.queue.numel(), self._s()))
@@ -101,10 +104,14 @@ class CudaShardBackend:
         check(self.lib.ffc_queue_scatter(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
                                          g_compact.data_ptr(), self._n, self.Ql, self.D, self.undo_rows.data_ptr() if save_undo else None, self._s()))
 
-    def restore(self):
+    def undo_bookkeeping(self):
+        """lru.py:252-255 + ffc.py:256-257: the LRU / queue positions of a rollback pass can be restored as soon as the probe
+        labels have been read (the sweep only needs labels, `ones` and the queue rows)."""
+        self.lru.undo(-1, self.qpos)
+
+    def restore_queue(self):
         check(self.lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
                                          self.undo_rows.data_ptr(), self._n, self.Ql, self.D, self._s()))
-        self.lru.undo(-1, self.qpos)
 
     def view(self, keys):
         return self.lru.view_batch(keys)
@@ -180,6 +187,7 @@ class ShardedFFCHead:
         self._stats = {}
         import os
         self._timing = [] if (os.environ.get('FFC_DIST_TIMING') and self._nccl) else None
+        self._side = torch.cuda.Stream(device=self.dev) if (self._nccl and not os.environ.get('FFC_DIST_NO_OVERLAP')) else None
 
     # -- helpers ----------------------------------------------------------------------------------
     def shard_of(self, keys):
@@ -246,15 +254,38 @@ class ShardedFFCHead:
         x_all, xl_all = self.gather(x, x_label)
         y_all, yl_all = self.gather(y, y_label)
         self._mark('all_gather')
-        l2, dx = self.head_pass_gathered(x_all, y_all, xl_all, yl_all, False)
+        ctx_rb = self._bookkeep(xl_all, yl_all, False, 0)
+        if self._nccl and self._side is not None:
+            # the commit pass's bookkeeping (LRU assign, probe labels) only needs the LRU state, which the rollback pass has
+            # already restored: run it on a side stream underneath the rollback pass's sweep
+            main = torch.cuda.current_stream(self.dev)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                timing, self._timing = self._timing, None
+                ctx_cm = self._bookkeep(yl_all, xl_all, True, 1)
+                self._timing = timing
+                ev_cm = torch.cuda.Event()
+                ev_cm.record(self._side)
+            for t in ctx_cm.values():
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+            l2, dx = self._finish(x_all, y_all, ctx_rb, False)
+            main.wait_event(ev_cm)
+        else:
+            l2, dx = self._finish(x_all, y_all, ctx_rb, False)
+            ctx_cm = self._bookkeep(yl_all, xl_all, True, 1)
         self._mark('start')
-        l1, dy = self.head_pass_gathered(y_all, x_all, yl_all, xl_all, True)
+        l1, dy = self._finish(y_all, x_all, ctx_cm, True)
         return l1 + l2, dx, dy
 
-    def head_pass_gathered(self, p_all, g_all, pl_all, gl_all, commit):
-        be, R, dev = self.backend, self.R, self.dev
-        n = p_all.shape[0]
-        # this rank's gallery keys, compacted in global batch order, without a host sync
+    def _bookkeep(self, pl_all, gl_all, commit, set_idx):
+        """Route this rank's gallery keys, run the LRU (+ immediate undo on a rollback pass) and resolve the probe labels.
+        Touches only LRU state and bookkeeping set `set_idx`; never the queue rows."""
+        be = self.backend
+        if hasattr(be, 'use_set'):
+            be.use_set(set_idx)
         mine = self.shard_of(gl_all) == self.rank
         order = torch.argsort((~mine).to(torch.int8), stable=True)
         n_mine = mine.sum().to(torch.int32).reshape(1)
@@ -262,13 +293,23 @@ class ShardedFFCHead:
         self._mark('route')
         be.assign(keys_c, n_mine, journal=not commit)
         self._mark('lru_assign')
-        be.scatter(g_all[order].contiguous(), save_undo=not commit)
-        self._mark('scatter')
         # probe labels: only the owner's LRU can know the key; everyone else answers -1
         loc = be.view(pl_all)
         label = torch.where(loc >= 0, loc + self.off, loc).to(torch.int32)
+        if not commit:
+            be.undo_bookkeeping()
         dist.all_reduce(label, op=dist.ReduceOp.MAX, group=self.group)
         self._mark('labels')
+        return dict(order=order, label=label, n_mine=n_mine, set=set_idx)
+
+    def _finish(self, p_all, g_all, ctx, commit):
+        be, R = self.backend, self.R
+        n = p_all.shape[0]
+        if hasattr(be, 'use_set'):
+            be.use_set(ctx['set'])
+        be.scatter(g_all[ctx['order']].contiguous(), save_undo=not commit)
+        self._mark('scatter')
+        label = ctx['label']
         st = self._stats.get(n)
         if st is None:
             st = self._stats[n] = be.new_stats(n, R)
@@ -294,11 +335,15 @@ class ShardedFFCHead:
         dp = self._reduce_scatter(dp_part)
         self._mark('reduce_scatter')
         if not commit:
-            be.restore()
+            be.restore_queue()
         be.end_pass()
         self._mark('restore')
-        self._last = dict(label=label, n_mine=n_mine)
+        self._last = dict(label=label, n_mine=ctx['n_mine'])
         return loss, dp
+
+    def head_pass_gathered(self, p_all, g_all, pl_all, gl_all, commit):
+        ctx = self._bookkeep(pl_all, gl_all, commit, 0)
+        return self._finish(p_all, g_all, ctx, commit)
 
     def head(self, p, g, probe_label, gallery_label, commit=True):
         return _ShardedFn.apply(p, self, g, probe_label, gallery_label, commit)
