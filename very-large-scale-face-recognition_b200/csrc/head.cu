@@ -29,6 +29,10 @@ struct ffc_head {
   float* thr;                  // [2][max_rows]
   int32_t* counts;             // [2] n_pos, n_out
   float* row_loss;             // [max_rows]
+  float* coef;                 // [4][max_rows] finalize coefficients
+  int32_t* nslot;              // [max_rows] hard-negative gather count
+  int32_t* wslot;              // [max_rows][2*KMAX]
+  uint8_t* wrow;               // [max_rows][2*KMAX]
   float* l_part;
   float* o_part;
   float* topv_part;
@@ -379,96 +383,107 @@ __device__ __forceinline__ float w_elem(const FinalizeArgs& a, int r, int64_t lo
   return a.use_bf16_rows ? __bfloat162float(a.qh[off]) : a.qf[off];
 }
 
-__global__ void __launch_bounds__(128) head_finalize_kernel(const FinalizeArgs a) {
-  const int i = blockIdx.x, n = a.n, D = a.D, k = a.k;
+// Pass 1, one THREAD per row: the scalar part of finalize (margin function, log/exp in fp64, top-k merge).  Doing this
+// per thread instead of on thread 0 of a per-row block keeps the fp64 transcendental latency off the critical path.
+__global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a, float* __restrict__ coef, int32_t* __restrict__ nslot,
+                                                            int32_t* __restrict__ wslot, uint8_t* __restrict__ wrow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = a.n, k = a.k;
+  if (i >= n) return;
   const int n_pos = a.counts[0], n_out = a.counts[1];
-  __shared__ float sh_coefO[2], sh_coefT[2];
-  __shared__ float sh_w[2 * KMAX];
-  __shared__ int32_t sh_slot[2 * KMAX];
-  __shared__ int sh_row[2 * KMAX];
-  __shared__ int sh_nw;
   const bool outl = a.is_out[i];
-  if (threadIdx.x == 0) {
-    float loss = 0.f;
-    sh_nw = 0;
-    if (!outl) {
-      const double s = a.scale, M = a.fixed_max, m = a.margin;
-      for (int l = 0; l < 2; ++l) {
-        double ct = a.tgt[l * n + i];
-        // bf16 operands are rounded, so a cosine of two (nearly) identical unit vectors can land a few ulp outside
-        // [-1, 1] and turn ffc.py:101's sqrt into NaN where the fp32 reference is finite: keep it strictly inside.
-        // The fp32 check mode does not clamp and propagates NaN exactly like the reference.
-        if (a.use_bf16_rows) ct = fmin(fmax(ct, -1.0 + 1e-6), 1.0 - 1e-6);
-        double ft, dft;
-        if (a.loss_type == FFC_LOSS_AM) {
-          ft = ct - m;
-          dft = 1.0;
-        } else if (a.loss_type == FFC_LOSS_ARC) {
-          const double sn = sqrt(1.0 - ct * ct);      // NaN for |ct| > 1, like ffc.py:101
-          ft = ct * cos(m) - sn * sin(m);
-          dft = cos(m) + ct * sin(m) / sn;
-        } else {
-          ft = ct > m ? ct - m : ct;
-          dft = 1.0;
-        }
-        const double zt = s * ft;
-        const double et = exp(zt - M);
-        const int cs = a.loss_type == FFC_LOSS_SV ? l : 0;   // common-statistics slot
-        const double L = (double)a.lsum[cs * n + i] + (double)a.lsum[(2 + l) * n + i] + et;
-        loss += (float)((log(L) + M - zt) / (double)n_pos);
-        sh_coefO[l] = (float)(s / L / (double)n_pos);
-        sh_coefT[l] = (float)(s * (et / L - 1.0) * dft / (double)n_pos);
+  float loss = 0.f;
+  float cO[2] = {0.f, 0.f}, cT[2] = {0.f, 0.f};
+  int nw = 0;
+  if (!outl) {
+    const double s = a.scale, M = a.fixed_max, m = a.margin;
+    for (int l = 0; l < 2; ++l) {
+      double ct = a.tgt[l * n + i];
+      // bf16 operands are rounded, so a cosine of two (nearly) identical unit vectors can land a few ulp outside
+      // [-1, 1] and turn ffc.py:101's sqrt into NaN where the fp32 reference is finite: keep it strictly inside.
+      // The fp32 check mode does not clamp and propagates NaN exactly like the reference.
+      if (a.use_bf16_rows) ct = fmin(fmax(ct, -1.0 + 1e-6), 1.0 - 1e-6);
+      double ft, dft;
+      if (a.loss_type == FFC_LOSS_AM) {
+        ft = ct - m;
+        dft = 1.0;
+      } else if (a.loss_type == FFC_LOSS_ARC) {
+        const double sn = sqrt(1.0 - ct * ct);      // NaN for |ct| > 1, like ffc.py:101
+        ft = ct * cos(m) - sn * sin(m);
+        dft = cos(m) + ct * sin(m) / sn;
+      } else {
+        ft = ct > m ? ct - m : ct;
+        dft = 1.0;
       }
-    } else {
-      // merge top-k candidates per loss: common (all ranks) + side_l (all ranks)
-      const float wneg = 1.f / ((float)n_out * (float)k);
-      for (int l = 0; l < 2; ++l) {
-        float tv[KMAX];
-        int32_t ti[KMAX];
-        for (int q = 0; q < KMAX; ++q) {
-          tv[q] = -INFINITY;
-          ti[q] = -1;
+      const double zt = s * ft;
+      const double et = exp(zt - M);
+      const int cs = a.loss_type == FFC_LOSS_SV ? l : 0;   // common-statistics slot
+      const double L = (double)a.lsum[cs * n + i] + (double)a.lsum[(2 + l) * n + i] + et;
+      loss += (float)((log(L) + M - zt) / (double)n_pos);
+      cO[l] = (float)(s / L / (double)n_pos);
+      cT[l] = (float)(s * (et / L - 1.0) * dft / (double)n_pos);
+    }
+  } else {
+    // merge top-k candidates per loss: common (all ranks) + side_l (all ranks)
+    const float wneg = 1.f / ((float)n_out * (float)k);
+    cO[0] = wneg;
+    for (int l = 0; l < 2; ++l) {
+      float tv[KMAX];
+      int32_t ti[KMAX];
+      for (int q = 0; q < KMAX; ++q) {
+        tv[q] = -INFINITY;
+        ti[q] = -1;
+      }
+      for (int r = 0; r < a.n_ranks; ++r)
+        for (int src = 0; src < 2; ++src) {
+          const int set = src == 0 ? 0 : 1 + l;
+          const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
+          for (int q = 0; q < k; ++q) {
+            const float v = a.topv[base + q];
+            // a side entry is tagged in bit 30: under loss 2 it reads queue[1]
+            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, (int32_t)(a.topi[base + q] | (src ? 0x40000000 : 0)));
+          }
         }
-        for (int r = 0; r < a.n_ranks; ++r)
-          for (int src = 0; src < 2; ++src) {
-            const int set = src == 0 ? 0 : 1 + l;
-            const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
-            for (int q = 0; q < k; ++q) {
-              const float v = a.topv[base + q];
-              // encode the source in the sign-free upper bit of a side index: side entries use W_l rows
-              if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, (int32_t)(a.topi[base + q] | (src ? 0x40000000 : 0)));
-            }
-          }
-        for (int q = 0; q < k; ++q) {
-          if (ti[q] < 0) continue;
-          const float v = tv[q];
-          loss += (v > 0.f ? v : 0.f) * wneg;
-          if (v >= 0.f) {
-            const int e = sh_nw++;
-            sh_w[e] = wneg;
-            sh_slot[e] = ti[q] & 0x3fffffff;
-            sh_row[e] = (ti[q] & 0x40000000) ? l : 0;   // side entry under loss 2 reads queue[1]
-          }
+      for (int q = 0; q < k; ++q) {
+        if (ti[q] < 0) continue;
+        const float v = tv[q];
+        loss += (v > 0.f ? v : 0.f) * wneg;
+        if (v >= 0.f) {
+          wslot[(int64_t)i * 2 * KMAX + nw] = ti[q] & 0x3fffffff;
+          wrow[(int64_t)i * 2 * KMAX + nw] = (ti[q] & 0x40000000) ? (uint8_t)l : (uint8_t)0;
+          ++nw;
         }
       }
     }
-    a.row_loss[i] = loss;
   }
-  __syncthreads();
+  a.row_loss[i] = loss;
+  coef[0 * n + i] = cO[0];
+  coef[1 * n + i] = cO[1];
+  coef[2 * n + i] = cT[0];
+  coef[3 * n + i] = cT[1];
+  nslot[i] = nw;
+}
+
+// Pass 2, one block per row: dLoss/dp from the accumulated sums (bandwidth bound).
+__global__ void __launch_bounds__(128) head_finalize_kernel(const FinalizeArgs a, const float* __restrict__ coef, const int32_t* __restrict__ nslot,
+                                                            const int32_t* __restrict__ wslot, const uint8_t* __restrict__ wrow) {
+  const int i = blockIdx.x, n = a.n, D = a.D;
+  const bool outl = a.is_out[i];
+  const float cO0 = coef[0 * n + i], cO1 = coef[1 * n + i], cT0 = coef[2 * n + i], cT1 = coef[3 * n + i];
   const int32_t tc = a.tcol[i];
   const int trow2 = (a.tpos[i] >= 0) ? 1 : 0;
-  const int nw = sh_nw;
+  const int nw = nslot[i];
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float g = 0.f;
     if (!outl) {
       const float oc0 = a.osum[((int64_t)0 * n + i) * D + d];
       const float oc1 = a.loss_type == FFC_LOSS_SV ? a.osum[((int64_t)1 * n + i) * D + d] : oc0;
-      g = sh_coefO[0] * (oc0 + a.osum[((int64_t)2 * n + i) * D + d]) + sh_coefO[1] * (oc1 + a.osum[((int64_t)3 * n + i) * D + d]);
-      if (tc >= 0) g += sh_coefT[0] * w_elem(a, 0, tc, d) + sh_coefT[1] * w_elem(a, trow2, tc, d);
+      g = cO0 * (oc0 + a.osum[((int64_t)2 * n + i) * D + d]) + cO1 * (oc1 + a.osum[((int64_t)3 * n + i) * D + d]);
+      if (tc >= 0) g += cT0 * w_elem(a, 0, tc, d) + cT1 * w_elem(a, trow2, tc, d);
     } else {
       for (int e = 0; e < nw; ++e) {
-        const int64_t loc = (int64_t)sh_slot[e] - a.col_offset;
-        if (loc >= 0 && loc < a.q_local) g += sh_w[e] * w_elem(a, sh_row[e], loc, d);
+        const int64_t loc = (int64_t)wslot[(int64_t)i * 2 * KMAX + e] - a.col_offset;
+        if (loc >= 0 && loc < a.q_local) g += cO0 * w_elem(a, wrow[(int64_t)i * 2 * KMAX + e], loc, d);
       }
     }
     a.dp[(int64_t)i * D + d] = g;
@@ -537,6 +552,10 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_CUDA(cudaMalloc(&h->thr, 2 * R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->counts, 2 * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->row_loss, R * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->coef, 4 * R * sizeof(float)));
+  FFC_CUDA(cudaMalloc(&h->nslot, R * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->wslot, R * 2 * KMAX * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->wrow, R * 2 * KMAX));
   FFC_CUDA(cudaMalloc(&h->l_part, h->part_rows_cap * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->o_part, h->part_rows_cap * D * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->topv_part, h->part_rows_cap * KMAX * sizeof(float)));
@@ -558,6 +577,10 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
   cudaFree(h->thr);
   cudaFree(h->counts);
   cudaFree(h->row_loss);
+  cudaFree(h->coef);
+  cudaFree(h->nslot);
+  cudaFree(h->wslot);
+  cudaFree(h->wrow);
   cudaFree(h->l_part);
   cudaFree(h->o_part);
   cudaFree(h->topv_part);
@@ -709,7 +732,9 @@ extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const f
   a.fixed_max = fixed_max_of(c);
   a.row_loss = h->row_loss;
   a.dp = dp_out;
-  head_finalize_kernel<<<a.n, 128, 0, s>>>(a);
+  head_row_coef_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
+  FFC_LAUNCH_CHECK();
+  head_finalize_kernel<<<a.n, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
   FFC_LAUNCH_CHECK();
   head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
   FFC_LAUNCH_CHECK();
