@@ -18,6 +18,7 @@
 // Synchronisation is all mbarriers: TMA -> MMA (full/empty rings), MMA -> epilogue (tcgen05.commit),
 // epilogue -> peer MMA (st.async complete_tx on the peer's mbarrier), peer MMA -> epilogue (multicast tcgen05.commit).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -29,10 +30,16 @@ namespace ffc {
 constexpr int BM = 128;            // probe rows per item
 constexpr int BN = 128;            // queue rows per tile
 constexpr int KC = 64;             // bf16 elements per 128-byte swizzle row
-constexpr int NS1 = 6;             // S-CTA W K-chunk stages (16 KB each)
+#ifndef FFC_NS1
+#define FFC_NS1 6
+#endif
+#ifndef FFC_JB
+#define FFC_JB 32
+#endif
+constexpr int NS1 = FFC_NS1;       // S-CTA W K-chunk stages (16 KB each)
 constexpr int NSB = 4;             // S accumulators in the S-CTA's TMEM (4 x 128 columns)
 constexpr int NPB = 3;             // P~ buffers in the O-CTA's shared memory
-constexpr int JB = 32;             // queue rows per O-CTA W stage
+constexpr int JB = FFC_JB;         // queue rows per O-CTA W stage
 constexpr int NEPI = 3;             // epilogue warpgroups in the S-CTA (tiles are dealt round-robin)
 constexpr int NTHREADS = 128 + NEPI * 128;   // 4 control warps + 12 epilogue warps
 constexpr int CHUNK1_BYTES = BN * KC * 2;   // 16384
@@ -171,6 +178,9 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32
                "r"(c), "r"(d), "r"(mbar)
                : "memory");
 }
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // tcgen05.commit that arrives on the barrier at the same offset in the CTAs of `cta_mask`
 __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -222,6 +232,8 @@ struct Sm100Params {
   float a2, b2;       // p~ = 2^(a2 * z - b2)
   int sv, k;
   int n_chunks, tiles_per_chunk, ns2;
+  int debug;   // bottleneck isolation, results are WRONG except 0 and 6 (FFC_SM100_DEBUG, see profiles/r1_bottleneck_isolation.md):
+               // 1 = O-CTA skips TMA+MMA, 2 = epilogue skips tcgen05.ld/exp, 3 = S-CTA skips TMA+MMA, 6 = plain remote stores
   float* l_part;
   float* o_part;
   float* topv_part;
@@ -253,6 +265,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   const int stage2_bytes = nkc * JB * KC * 2;   // D/64 boxes of 4 KB
   const int n_nhalf = (D + 255) / 256;          // GEMM-2 instructions per K step (N <= 256 each)
   const int n2 = D < 256 ? D : 256;
+  // P~ hand-off flavour: st.async (per-store complete_tx on the peer's mbarrier) or plain remote stores + one
+  // fence/arrive per warp and tile (FFC_SM100_DEBUG=6)
+  const bool plain_st = prm.debug == 6;
 
   unsigned char* sP = smem + OFF_DATA;                         // S-CTA
   unsigned char* sW1 = sP + nkc * CHUNK1_BYTES;                // S-CTA
@@ -271,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     }
     for (int i = 0; i < NPB; ++i) {
       mbar_init(&bars.pt_empty[i], 1);
-      mbar_init(&bars.pt_full[i], 1);
+      mbar_init(&bars.pt_full[i], plain_st ? 4 : 1);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bars.w2_full[i], 1);
@@ -294,7 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   if (rank == 0) {
     // =========================================== S-CTA ===========================================
     if (warp == 0) {
-      if (lane == 0 && n_tiles > 0) {
+      if (lane == 0 && n_tiles > 0 && prm.debug != 3) {
         mbar_expect_tx(&bars.p_full, (uint32_t)(nkc * CHUNK1_BYTES));
         for (int kc = 0; kc < nkc; ++kc) tma_load_2d(&map_p, &bars.p_full, sP + kc * CHUNK1_BYTES, kc * KC, row0);
         int stage = 0;
@@ -314,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     } else if (warp == 1) {
       if (lane == 0 && n_tiles > 0) {
         constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-        mbar_wait(&bars.p_full, 0);
+        if (prm.debug != 3) mbar_wait(&bars.p_full, 0);
         tc_fence_after();
         int stage = 0;
         uint32_t ph = 0;
@@ -323,6 +338,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           const uint32_t use = (uint32_t)(i / NSB);
           mbar_wait(&bars.s_empty[sb], (use & 1) ^ 1);
           tc_fence_after();
+          if (prm.debug == 3) {
+            mbar_arrive(&bars.s_full[sb]);
+            continue;
+          }
           const uint32_t tmem_s = tmem_base + (uint32_t)(sb * BN);
           for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(&bars.w_full[stage], ph);
@@ -396,10 +415,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll 1
           for (int cc = 0; cc < BN / 32; ++cc) {
             uint32_t v[32];
-            tc_ld32(tmem_s + cc * 32, v);
+            if (prm.debug == 2) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = 0u;
+            } else {
+              tc_ld32(tmem_s + cc * 32, v);
+            }
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
+              if (prm.debug == 2) {
+                pk[c >> 1] = 0u;
+                continue;
+              }
               const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
               float p0, p1, g0, g1;
               if (SV) {
@@ -420,7 +448,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t chunk16 = (uint32_t)((cc & 1) * 4 + q);
-              st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              if (plain_st)
+                st_cluster_v4(base + ((chunk16 ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              else
+                st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
           }
           lsum += l0 + l1;
@@ -505,13 +536,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const uint32_t chunk16 = (uint32_t)((cc & 3) * 2 + q);
-            st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            if (plain_st)
+              st_cluster_v4(base + ((chunk16 ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            else
+              st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
         // S buffer sb may be overwritten by a later tile's MMA
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
+        if (plain_st) {   // publish this warp's rows of P~ (generic-proxy remote writes -> async-proxy reads in the peer)
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(ptfull_remote);
+        }
       }
       // ---- per-row partials: combine the two warpgroups through shared memory ----
       float* stage_v = reinterpret_cast<float*>(sW1);                             // [2][128][KMAX] (W ring is idle now)
@@ -572,7 +611,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   } else {
     // =========================================== O-CTA ===========================================
     if (warp == 0) {
-      if (lane == 0 && n_tiles > 0) {
+      if (lane == 0 && n_tiles > 0 && prm.debug != 1) {
         int stage = 0;
         uint32_t ph = 0;
         for (int t = t_begin; t < t_end; ++t) {
@@ -597,10 +636,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           const int pb = i % NPB;
           const uint32_t use = (uint32_t)(i / NPB);
           // this thread is the single arriver of pt_full[pb]; the 32 KB of P~ arrive as st.async complete_tx bytes
-          mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);
+          if (!plain_st) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);
           mbar_wait_cluster(&bars.pt_full[pb], use & 1);
           asm volatile("fence.proxy.async;" ::: "memory");
           tc_fence_after();
+          if (prm.debug == 1) {
+            mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb]), 0));
+            continue;
+          }
           const uint32_t a_base = smem_u32(sPt + pb * PT_BYTES);
           for (int jb = 0; jb < BN / JB; ++jb) {
             mbar_wait(&bars.w2_full[stage], ph);
@@ -624,7 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           }
           tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);   // frees P~ buffer pb: arrives in the S-CTA (cluster rank 0)
         }
-        tc_commit(&bars.o_full);
+        if (prm.debug == 1) mbar_arrive(&bars.o_full); else tc_commit(&bars.o_full);
         mbar_wait(&bars.o_full, 0);     // one polling thread; the 8 epilogue warps block on a hardware barrier instead
       }
       __syncwarp();
@@ -756,7 +799,7 @@ int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
 
 static int ns2_for(int D) {
   const int stage = (D / KC) * JB * KC * 2;
-  int ns = (int)((200 * 1024 - NPB * PT_BYTES) / stage);
+  int ns = (int)((225 * 1024 - NPB * PT_BYTES) / stage);
   return ns > 8 ? 8 : (ns < 2 ? 2 : ns);
 }
 
@@ -786,6 +829,10 @@ int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cu
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(a.n_cols, BN));
   p.tiles_per_chunk = (int)ceil_div64(n_tiles, a.n_chunks);
   p.ns2 = ns2_for(a.D);
+  {
+    const char* dbg = getenv("FFC_SM100_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   p.l_part = a.l_part;
   p.o_part = a.o_part;
   p.topv_part = a.topv_part;

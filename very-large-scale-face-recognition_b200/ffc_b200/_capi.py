@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libffc_b200.so')
+LIB_PATH = os.environ.get('FFC_B200_LIB', os.path.join(_HERE, 'libffc_b200.so'))   # override: kernel-variant experiments only
 
 LOSS_TYPES = {'AM': 0, 'Arc': 1, 'SV': 2}
 PRECISIONS = {'bf16': 0, 'fp32': 1}
