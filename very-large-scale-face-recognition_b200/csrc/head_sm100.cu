@@ -125,6 +125,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
                "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -206,13 +211,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 }
 
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): SWIZZLE_128B, version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
-  d |= (uint64_t)2 << 61;   // layout_type = SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 0 = SWIZZLE_NONE (interleaved 8x16-byte core matrices)
   return d;
 }
 // instruction descriptor (InstrDescriptor): bf16 x bf16 -> f32
@@ -221,8 +226,27 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Byte offset of the 16-byte piece `piece` (= 8 consecutive queue columns, 0..15) of row `r` inside one 32 KB P~ buffer:
+// the interleaved (SWIZZLE_NONE) K-major layout, 8x16-byte core matrices with the 128 rows of one piece contiguous
+// (2 KB).  The 32 lanes of a warp (32 consecutive rows) therefore write 512 contiguous bytes per store instruction --
+// coalesced DSMEM traffic (hand-off alone: 0.80 ms per sweep, against 1.47 ms for 128-byte-strided SWIZZLE_128B rows).
+__device__ __forceinline__ uint32_t pt_offset(uint32_t piece, uint32_t r) { return piece * (uint32_t)(BM * 16) + r * 16u; }
+
+// One lane of a converged warp; the warp stays converged, so descriptors live in uniform registers and consecutive
+// tcgen05.mma issue back to back.  (Issuing from an `if (lane == 0)` region makes every MMA pay a vote loop plus
+// register->uniform moves: 125-220 cycles per instruction against the 64 / 128 cycles the tensor pipe needs.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+#ifndef FFC_SM100_DEBUG_BUILD
+#define FFC_SM100_DEBUG_BUILD 0     // 1: honour Sm100Params::debug (bottleneck isolation, see tools/sweep_modes.py)
+#endif
+
 struct Sm100Params {
-  int n_rows, D;
+  int n_rows;
   int64_t n_cols;
   const int32_t* n_cols_dev;
   const int32_t* tcol;
@@ -230,20 +254,37 @@ struct Sm100Params {
   const float* thr;
   const uint8_t* is_out;
   float a2, b2;       // p~ = 2^(a2 * z - b2)
-  int sv, k;
-  int n_chunks, tiles_per_chunk, ns2;
-  int debug;   // bottleneck isolation, results are WRONG except 0 and 6 (FFC_SM100_DEBUG, see profiles/r1_bottleneck_isolation.md):
-               // 1 = O-CTA skips TMA+MMA, 2 = epilogue skips tcgen05.ld/exp, 3 = S-CTA skips TMA+MMA, 6 = plain remote stores
+  int k;
+  int n_chunks, tiles_per_chunk;
+  int debug;   // bottleneck isolation BITMASK, only in FFC_SM100_DEBUG_BUILD builds; results are WRONG when any bit is set:
+               // 1 = O-CTA skips TMA+MMA, 2 = epilogue skips tcgen05.ld/exp, 4 = S-CTA skips TMA+MMA,
+               // 16 = no P~ hand-off (both CTAs free-run), 64 = no W TMA loads (MMAs run on whatever is in shared memory)
   float* l_part;
   float* o_part;
   float* topv_part;
   int32_t* topi_part;
 };
 
-template <bool SV>
+template <int D>
+struct SweepShape {
+  static constexpr int NKC = D / KC;                         // 64-column K chunks of the feature dim
+  static constexpr int STAGE2_BYTES = NKC * JB * KC * 2;     // O-CTA stage: JB queue rows x D
+  static constexpr int NS2_RAW = (225 * 1024 - NPB * PT_BYTES) / STAGE2_BYTES;
+  static constexpr int NS2 = NS2_RAW > 8 ? 8 : (NS2_RAW < 2 ? 2 : NS2_RAW);
+  static constexpr int N2 = D < 256 ? D : 256;               // GEMM-2 instruction N
+  static constexpr int NHALF = (D + 255) / 256;              // GEMM-2 instructions per K step
+  static constexpr size_t SMEM_S = OFF_DATA + (size_t)NKC * CHUNK1_BYTES + (size_t)NS1 * CHUNK1_BYTES;
+  static constexpr size_t SMEM_O = OFF_DATA + NPB * (size_t)PT_BYTES + (size_t)NS2 * STAGE2_BYTES;
+  static constexpr size_t SMEM = (SMEM_S > SMEM_O ? SMEM_S : SMEM_O) + 1024;   // slack for the 1024-byte alignment of the base
+  static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+};
+
+template <bool SV, int D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     ffc_head_sweep_sm100_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_w1,
                                 const __grid_constant__ CUtensorMap map_w2, const Sm100Params prm) {
+  using Sh = SweepShape<D>;
+  constexpr int NKC = Sh::NKC;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B operands need a 1024-byte aligned base; both CTAs of the pair compute the same offset
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -254,23 +295,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   const int n_row_tiles = (prm.n_rows + BM - 1) / BM;
   const int rt = item % n_row_tiles, chunk = item / n_row_tiles;
   const int row0 = rt * BM;
-  const int D = prm.D, nkc = D / KC;
   const int64_t n_cols = prm.n_cols_dev ? (int64_t)*prm.n_cols_dev : prm.n_cols;
   const int n_tiles_total = (int)((n_cols + BN - 1) / BN);
   const int t_begin = chunk * prm.tiles_per_chunk;
   int t_end = t_begin + prm.tiles_per_chunk;
   if (t_end > n_tiles_total) t_end = n_tiles_total;
   const int n_tiles = t_end > t_begin ? t_end - t_begin : 0;
-  const int ns2 = prm.ns2;
-  const int stage2_bytes = nkc * JB * KC * 2;   // D/64 boxes of 4 KB
-  const int n_nhalf = (D + 255) / 256;          // GEMM-2 instructions per K step (N <= 256 each)
-  const int n2 = D < 256 ? D : 256;
-  // P~ hand-off flavour: st.async (per-store complete_tx on the peer's mbarrier) or plain remote stores + one
-  // fence/arrive per warp and tile (FFC_SM100_DEBUG=6)
-  const bool plain_st = prm.debug == 6;
+  const int dbg = FFC_SM100_DEBUG_BUILD ? prm.debug : 0;
+  const bool dbg_noO = (dbg & 1) != 0, dbg_noEpi = (dbg & 2) != 0, dbg_noS = (dbg & 4) != 0, dbg_noHand = (dbg & 16) != 0, dbg_noTma = (dbg & 64) != 0;
 
   unsigned char* sP = smem + OFF_DATA;                         // S-CTA
-  unsigned char* sW1 = sP + nkc * CHUNK1_BYTES;                // S-CTA
+  unsigned char* sW1 = sP + NKC * CHUNK1_BYTES;                // S-CTA
   unsigned char* sPt = smem + OFF_DATA;                        // O-CTA
   unsigned char* sW2 = sPt + NPB * PT_BYTES;                   // O-CTA
 
@@ -286,7 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     }
     for (int i = 0; i < NPB; ++i) {
       mbar_init(&bars.pt_empty[i], 1);
-      mbar_init(&bars.pt_full[i], plain_st ? 4 : 1);
+      mbar_init(&bars.pt_full[i], 1);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bars.w2_full[i], 1);
@@ -309,16 +344,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   if (rank == 0) {
     // =========================================== S-CTA ===========================================
     if (warp == 0) {
-      if (lane == 0 && n_tiles > 0 && prm.debug != 3) {
-        mbar_expect_tx(&bars.p_full, (uint32_t)(nkc * CHUNK1_BYTES));
-        for (int kc = 0; kc < nkc; ++kc) tma_load_2d(&map_p, &bars.p_full, sP + kc * CHUNK1_BYTES, kc * KC, row0);
+      // ---- TMA producer (converged warp, one elected lane issues) ----
+      if (n_tiles > 0 && !dbg_noS) {
+        if (elect_one()) {
+          mbar_expect_tx(&bars.p_full, (uint32_t)(NKC * CHUNK1_BYTES));
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&map_p, &bars.p_full, sP + kc * CHUNK1_BYTES, kc * KC, row0);
+        }
+        __syncwarp();
         int stage = 0;
         uint32_t ph = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-          for (int kc = 0; kc < nkc; ++kc) {
+        for (int t = t_begin; t < t_end && !dbg_noTma; ++t) {
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) {
             mbar_wait(&bars.w_empty[stage], ph ^ 1);
-            mbar_expect_tx(&bars.w_full[stage], CHUNK1_BYTES);
-            tma_load_2d(&map_w1, &bars.w_full[stage], sW1 + stage * CHUNK1_BYTES, kc * KC, t * BN);
+            if (elect_one()) {
+              mbar_expect_tx(&bars.w_full[stage], CHUNK1_BYTES);
+              tma_load_2d(&map_w1, &bars.w_full[stage], sW1 + stage * CHUNK1_BYTES, kc * KC, t * BN);
+            }
+            __syncwarp();
             if (++stage == NS1) {
               stage = 0;
               ph ^= 1;
@@ -327,38 +371,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         }
       }
     } else if (warp == 1) {
-      if (lane == 0 && n_tiles > 0) {
+      // ---- GEMM-1 issue: S[128 x 128] = P[128 x D] . W_tile[128 x D]^T, 4 x (K = 16) per 64-column chunk ----
+      if (n_tiles > 0) {
         constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-        if (prm.debug != 3) mbar_wait(&bars.p_full, 0);
+        if (!dbg_noS) mbar_wait(&bars.p_full, 0);
         tc_fence_after();
+        const uint64_t a0 = make_desc(smem_u32(sP), 16, 1024);
+        const uint64_t b0 = make_desc(smem_u32(sW1), 16, 1024);
         int stage = 0;
         uint32_t ph = 0;
         for (int i = 0; i < n_tiles; ++i) {
           const int sb = i & (NSB - 1);
-          const uint32_t use = (uint32_t)(i / NSB);
-          mbar_wait(&bars.s_empty[sb], (use & 1) ^ 1);
+          mbar_wait(&bars.s_empty[sb], ((uint32_t)(i / NSB) & 1) ^ 1);
           tc_fence_after();
-          if (prm.debug == 3) {
-            mbar_arrive(&bars.s_full[sb]);
+          if (dbg_noS) {
+            if (elect_one()) mbar_arrive(&bars.s_full[sb]);
+            __syncwarp();
             continue;
           }
           const uint32_t tmem_s = tmem_base + (uint32_t)(sb * BN);
-          for (int kc = 0; kc < nkc; ++kc) {
-            mbar_wait(&bars.w_full[stage], ph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(sP + kc * CHUNK1_BYTES);
-            const uint32_t b_addr = smem_u32(sW1 + stage * CHUNK1_BYTES);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              tc_mma(tmem_s, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc, (kc | k) ? 1u : 0u);
+          for (int kc = 0; kc < NKC; ++kc) {
+            if (!dbg_noTma) {
+              mbar_wait(&bars.w_full[stage], ph);
+              tc_fence_after();
             }
-            tc_commit(&bars.w_empty[stage]);
+            if (elect_one()) {
+              const uint64_t ad = a0 + (uint64_t)(kc * (CHUNK1_BYTES >> 4));
+              const uint64_t bd = b0 + (uint64_t)(stage * (CHUNK1_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) tc_mma(tmem_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+              if (!dbg_noTma) tc_commit(&bars.w_empty[stage]);
+              if (kc == NKC - 1) tc_commit(&bars.s_full[sb]);
+            }
+            __syncwarp();
             if (++stage == NS1) {
               stage = 0;
               ph ^= 1;
             }
           }
-          tc_commit(&bars.s_full[sb]);
         }
       }
     } else if (warp >= 4) {
@@ -389,7 +440,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       int kth = 0;
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
-      const uint32_t sw = (uint32_t)(r_local & 7);
       // tile i uses S buffer i % NSB and P~ buffer i % NPB; NEPI == NPB, so this warpgroup always writes P~ buffer g
       static_assert(NEPI == NPB, "epilogue warpgroups and P~ buffers are paired");
       const int pb = g;
@@ -402,7 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         if (prm.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(prm.cmask + (j0 >> 5)));
         mbar_wait(&bars.s_full[sb], (uint32_t)(i / NSB) & 1);
         tc_fence_after();
-        mbar_wait(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
+        if (!dbg_noHand) mbar_wait(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
         const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
         const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
         const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
@@ -415,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll 1
           for (int cc = 0; cc < BN / 32; ++cc) {
             uint32_t v[32];
-            if (prm.debug == 2) {
+            if (dbg_noEpi) {
 #pragma unroll
               for (int c = 0; c < 32; ++c) v[c] = 0u;
             } else {
@@ -424,7 +474,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-              if (prm.debug == 2) {
+              if (dbg_noEpi) {
                 pk[c >> 1] = 0u;
                 continue;
               }
@@ -444,14 +494,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               l1 += p1;
               pk[c >> 1] = pack_bf16(g0, g1);
             }
-            const uint32_t base = pt_remote + (uint32_t)((cc >> 1) * (BM * 128)) + (uint32_t)(r_local * 128);
+            // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
+            if (!dbg_noHand) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t chunk16 = (uint32_t)((cc & 1) * 4 + q);
-              if (plain_st)
-                st_cluster_v4(base + ((chunk16 ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-              else
-                st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              for (int q = 0; q < 4; ++q)
+                st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 4 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
+                            pk[4 * q + 3]);
             }
           }
           lsum += l0 + l1;
@@ -530,29 +578,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             lsum += p0 + p1;
             pk[c >> 1] = pack_bf16(g0, g1);
           }
-          // P~[r_local][cc*16 .. +16) as 2 x 16-byte chunks, K-major SWIZZLE_128B: 64-column sub-tiles of 16 KB.
-          // st.async: each 16-byte store counts itself on the peer's pt_full[pb] (32 KB per tile in total).
-          const uint32_t base = pt_remote + (uint32_t)((cc >> 2) * (BM * 128)) + (uint32_t)(r_local * 128);
+          // P~[r_local][cc*16 .. +16) = 2 pieces of 16 bytes (st.async, 32 KB per tile in total on pt_full[pb])
+          if (!dbg_noHand) {
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint32_t chunk16 = (uint32_t)((cc & 3) * 2 + q);
-            if (plain_st)
-              st_cluster_v4(base + ((chunk16 ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            else
-              st_async_v4(base + ((chunk16 ^ sw) << 4), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            for (int q = 0; q < 2; ++q)
+              st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 2 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
+                          pk[4 * q + 3]);
           }
         }
         // S buffer sb may be overwritten by a later tile's MMA
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
-        if (plain_st) {   // publish this warp's rows of P~ (generic-proxy remote writes -> async-proxy reads in the peer)
-          asm volatile("fence.proxy.async;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(ptfull_remote);
-        }
       }
-      // ---- per-row partials: combine the two warpgroups through shared memory ----
+      // ---- per-row partials: combine the three warpgroups through shared memory ----
       float* stage_v = reinterpret_cast<float*>(sW1);                             // [2][128][KMAX] (W ring is idle now)
       int32_t* stage_i = reinterpret_cast<int32_t*>(sW1 + 2 * BM * KMAX * 4);
       float* stage_l = reinterpret_cast<float*>(sW1 + 4 * BM * KMAX * 4);         // [2][128]
@@ -611,16 +650,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   } else {
     // =========================================== O-CTA ===========================================
     if (warp == 0) {
-      if (lane == 0 && n_tiles > 0 && prm.debug != 1) {
+      // ---- TMA producer: one 3-D box (64 features x JB queue rows x D/64 feature chunks) per stage ----
+      if (n_tiles > 0 && !dbg_noO && !dbg_noTma) {
         int stage = 0;
         uint32_t ph = 0;
         for (int t = t_begin; t < t_end; ++t) {
+#pragma unroll
           for (int jb = 0; jb < BN / JB; ++jb) {
             mbar_wait(&bars.w2_empty[stage], ph ^ 1);
-            mbar_expect_tx(&bars.w2_full[stage], (uint32_t)stage2_bytes);
-            unsigned char* dst = sW2 + stage * stage2_bytes;
-            for (int kc = 0; kc < nkc; ++kc) tma_load_2d(&map_w2, &bars.w2_full[stage], dst + kc * (JB * 128), kc * KC, t * BN + jb * JB);
-            if (++stage == ns2) {
+            if (elect_one()) {
+              mbar_expect_tx(&bars.w2_full[stage], (uint32_t)Sh::STAGE2_BYTES);
+              tma_load_3d(&map_w2, &bars.w2_full[stage], sW2 + stage * Sh::STAGE2_BYTES, 0, t * BN + jb * JB, 0);
+            }
+            __syncwarp();
+            if (++stage == Sh::NS2) {
               stage = 0;
               ph ^= 1;
             }
@@ -628,47 +671,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         }
       }
     } else if (warp == 1) {
-      if (lane == 0 && n_tiles > 0) {
-        const uint32_t idesc = make_idesc(BM, n2, 0, 1);
-        int stage = 0;
-        uint32_t ph = 0;
+      // ---- GEMM-2 issue: O[128 x D] += P~[128 x 128] . W_tile[128 x D]; per K = 16 queue rows one MMA per 256 features ----
+      if (n_tiles > 0) {
+        constexpr uint32_t idesc = make_idesc(BM, Sh::N2, 0, 1);
+        // A = P~: interleaved core matrices, K halves 2 KB apart (LBO), 8-row groups 128 B apart (SBO)
+        const uint64_t a0 = make_desc(smem_u32(sPt), BM * 16, 128, 0);
+        // B = W stage, MN-major (N = feature dim): 64-feature atoms JB*128 bytes apart (LBO), 8-row groups 1 KB apart (SBO)
+        const uint64_t b0 = make_desc(smem_u32(sW2), JB * 128, 1024);
+        int stage = 0, pb = 0;
+        uint32_t ph = 0, pt_ph = 0;
         for (int i = 0; i < n_tiles; ++i) {
-          const int pb = i % NPB;
-          const uint32_t use = (uint32_t)(i / NPB);
-          // this thread is the single arriver of pt_full[pb]; the 32 KB of P~ arrive as st.async complete_tx bytes
-          if (!plain_st) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);
-          mbar_wait_cluster(&bars.pt_full[pb], use & 1);
+          if (!dbg_noHand) {
+            // this lane is the single arriver of pt_full[pb]; the 32 KB of P~ arrive as st.async complete_tx bytes
+            if (elect_one()) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);
+            __syncwarp();
+            mbar_wait_cluster(&bars.pt_full[pb], pt_ph);
+          }
           asm volatile("fence.proxy.async;" ::: "memory");
           tc_fence_after();
-          if (prm.debug == 1) {
-            mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb]), 0));
-            continue;
-          }
-          const uint32_t a_base = smem_u32(sPt + pb * PT_BYTES);
-          for (int jb = 0; jb < BN / JB; ++jb) {
-            mbar_wait(&bars.w2_full[stage], ph);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(sW2 + stage * stage2_bytes);
+          if (dbg_noO) {
+            if (!dbg_noHand && elect_one()) mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb]), 0));
+            __syncwarp();
+          } else {
+            const uint64_t ap = a0 + (uint64_t)(pb * (PT_BYTES >> 4));
 #pragma unroll
-            for (int k16 = 0; k16 < JB / 16; ++k16) {
-              const int kk = jb * JB + k16 * 16;                                    // queue row within the tile
-              const uint64_t adesc = make_desc(a_base + (uint32_t)((kk >> 6) * (BM * 128)) + (uint32_t)(((kk & 63) >> 4) * 32), 16, 1024);
-              for (int nh = 0; nh < n_nhalf; ++nh) {
-                // B: MN-major (N = feature dim), 64-wide atoms JB*128 bytes apart (LBO), 8-row groups 1024 bytes apart (SBO)
-                const uint64_t bdesc = make_desc(b_base + (uint32_t)(nh * 4 * (JB * 128)) + (uint32_t)(k16 * 16 * 128), JB * 128, 1024);
-                tc_mma(tmem_base + (uint32_t)(nh * 256), adesc, bdesc, idesc, (i | jb | k16) ? 1u : 0u);
+            for (int jb = 0; jb < BN / JB; ++jb) {
+              if (!dbg_noTma) {
+                mbar_wait(&bars.w2_full[stage], ph);
+                tc_fence_after();
+              }
+              if (elect_one()) {
+                const uint64_t bs = b0 + (uint64_t)(stage * (Sh::STAGE2_BYTES >> 4));
+#pragma unroll
+                for (int k16 = 0; k16 < JB / 16; ++k16) {
+                  const int kk = jb * JB + k16 * 16;                                    // queue row within the tile
+                  const uint64_t ad = ap + (uint64_t)((kk >> 3) * ((BM * 16) >> 4));
+#pragma unroll
+                  for (int nh = 0; nh < Sh::NHALF; ++nh) {
+                    const uint64_t bd = bs + (uint64_t)(nh * 4 * ((JB * 128) >> 4) + k16 * ((16 * 128) >> 4));
+                    tc_mma(tmem_base + (uint32_t)(nh * 256), ad, bd, idesc, (i | jb | k16) ? 1u : 0u);
+                  }
+                }
+                if (!dbg_noTma) tc_commit(&bars.w2_empty[stage]);
+                // frees P~ buffer pb: arrives in the S-CTA (cluster rank 0)
+                if (jb == BN / JB - 1 && !dbg_noHand) tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);
+              }
+              __syncwarp();
+              if (++stage == Sh::NS2) {
+                stage = 0;
+                ph ^= 1;
               }
             }
-            tc_commit(&bars.w2_empty[stage]);
-            if (++stage == ns2) {
-              stage = 0;
-              ph ^= 1;
-            }
           }
-          tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);   // frees P~ buffer pb: arrives in the S-CTA (cluster rank 0)
+          if (++pb == NPB) {
+            pb = 0;
+            pt_ph ^= 1;
+          }
         }
-        if (prm.debug == 1) mbar_arrive(&bars.o_full); else tc_commit(&bars.o_full);
-        mbar_wait(&bars.o_full, 0);     // one polling thread; the 8 epilogue warps block on a hardware barrier instead
+        if (elect_one()) {
+          if (dbg_noO) mbar_arrive(&bars.o_full); else tc_commit(&bars.o_full);
+        }
+        __syncwarp();
+        mbar_wait(&bars.o_full, 0);     // one polling warp; the 8 epilogue warps block on a hardware barrier instead
       }
       __syncwarp();
       asm volatile("bar.sync 2, 288;" ::: "memory");
@@ -681,7 +745,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const bool row_ok = row < prm.n_rows;
       asm volatile("bar.sync 2, 288;" ::: "memory");   // released by the MMA warp once every tcgen05.mma of the item has completed
       tc_fence_after();
-      const int half = D / 2;                      // D is a multiple of 64
+      constexpr int half = D / 2;                  // D is a multiple of 64
       float* dst = prm.o_part + ((int64_t)chunk * prm.n_rows + (row_ok ? row : 0)) * D + g * half;
       for (int c0 = 0; c0 < half; c0 += 32) {
         uint32_t v[32];
@@ -737,14 +801,13 @@ struct MapKey {
 struct Sm100Cache {
   PFN_encodeTiled encode = nullptr;
   std::vector<std::pair<MapKey, CUtensorMap>> maps;
-  bool attr_set = false;
 };
 
 Sm100Cache* sm100_cache_create() { return new Sm100Cache(); }
 void sm100_cache_destroy(Sm100Cache* c) { delete c; }
 
-static int get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_rows, CUtensorMap* out) {
-  MapKey key{ptr, rows, D, box_rows};
+static int get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_rows, bool chunked3d, CUtensorMap* out) {
+  MapKey key{ptr, rows, D, chunked3d ? -box_rows : box_rows};
   for (auto& e : c->maps)
     if (e.first == key) {
       *out = e.second;
@@ -758,14 +821,27 @@ static int get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_
     c->encode = (PFN_encodeTiled)fn;
   }
   CUtensorMap m;
-  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (!chunked3d) {
+    // [rows, D] bf16 row-major; box = 64 features (one 128-byte swizzle row) x box_rows
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // the same matrix seen as [D/64 chunks][rows][64]: one box = (64 features, box_rows rows, all D/64 chunks) lands in
+    // shared memory chunk-major, i.e. D/64 consecutive [box_rows x 128 B] swizzled slabs -- a whole GEMM-2 stage per TMA
+    cuuint64_t dims[3] = {(cuuint64_t)KC, (cuuint64_t)rows, (cuuint64_t)(D / KC)};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)KC * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, (cuuint32_t)(D / KC)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with %d (ptr=%p rows=%lld D=%d box_rows=%d)", (int)r, ptr, (long long)rows, D, box_rows);
+    set_error("cuTensorMapEncodeTiled failed with %d (ptr=%p rows=%lld D=%d box_rows=%d 3d=%d)", (int)r, ptr, (long long)rows, D, box_rows, (int)chunked3d);
     return FFC_ERR_CUDA;
   }
   if (c->maps.size() > 64) c->maps.clear();
@@ -797,24 +873,31 @@ int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
   return best;
 }
 
-static int ns2_for(int D) {
-  const int stage = (D / KC) * JB * KC * 2;
-  int ns = (int)((225 * 1024 - NPB * PT_BYTES) / stage);
-  return ns > 8 ? 8 : (ns < 2 ? 2 : ns);
+template <bool SV, int D>
+static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUtensorMap& mw2, const Sm100Params& p, int n_items, cudaStream_t s) {
+  static bool attr_set = false;
+  auto kern = ffc_head_sweep_sm100_kernel<SV, D>;
+  constexpr size_t smem = SweepShape<D>::SMEM;
+  if (!attr_set) {
+    FFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<dim3(2 * n_items), dim3(NTHREADS), smem, s>>>(mp, mw1, mw2, p);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
 }
 
 int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cudaStream_t s) {
   (void)cache_slot;
-  FFC_REQUIRE(a.D % 64 == 0 && a.D >= 64 && a.D <= 512 && (a.D & (a.D - 1)) == 0, "tcgen05 sweep: D=%d must be 64, 128, 256 or 512", a.D);
+  FFC_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256 || a.D == 512, "tcgen05 sweep: D=%d must be 64, 128, 256 or 512", a.D);
   FFC_REQUIRE(a.W_bf16 && a.P_bf16, "tcgen05 sweep: bf16 operands missing");
   CUtensorMap mp, mw1, mw2;
   int rc;
-  if ((rc = get_map(cache, a.P_bf16, a.n_rows, a.D, BM, &mp))) return rc;
-  if ((rc = get_map(cache, a.W_bf16, a.n_cols, a.D, BN, &mw1))) return rc;
-  if ((rc = get_map(cache, a.W_bf16, a.n_cols, a.D, JB, &mw2))) return rc;
+  if ((rc = get_map(cache, a.P_bf16, a.n_rows, a.D, BM, false, &mp))) return rc;
+  if ((rc = get_map(cache, a.W_bf16, a.n_cols, a.D, BN, false, &mw1))) return rc;
+  if ((rc = get_map(cache, a.W_bf16, a.n_cols, a.D, JB, true, &mw2))) return rc;
   Sm100Params p;
   p.n_rows = a.n_rows;
-  p.D = a.D;
   p.n_cols = a.n_cols;
   p.n_cols_dev = a.n_cols_dev;
   p.tcol = a.tcol;
@@ -823,39 +906,34 @@ int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cu
   p.is_out = a.is_out;
   p.a2 = a.scale * LOG2E;
   p.b2 = a.fixed_max * LOG2E;
-  p.sv = a.sv;
   p.k = a.k;
   p.n_chunks = a.n_chunks;
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(a.n_cols, BN));
   p.tiles_per_chunk = (int)ceil_div64(n_tiles, a.n_chunks);
-  p.ns2 = ns2_for(a.D);
+  p.debug = 0;
+#if FFC_SM100_DEBUG_BUILD
   {
     const char* dbg = getenv("FFC_SM100_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+#endif
   p.l_part = a.l_part;
   p.o_part = a.o_part;
   p.topv_part = a.topv_part;
   p.topi_part = a.topi_part;
-  const int nkc = a.D / KC;
-  const size_t smem_s = OFF_DATA + (size_t)nkc * CHUNK1_BYTES + (size_t)NS1 * CHUNK1_BYTES;
-  const size_t smem_o = OFF_DATA + NPB * (size_t)PT_BYTES + (size_t)p.ns2 * nkc * JB * KC * 2;
-  const size_t smem = std::max(smem_s, smem_o) + 1024;   // slack for the 1024-byte alignment of the dynamic base
-  FFC_REQUIRE(smem <= 227 * 1024, "tcgen05 sweep: shared memory budget exceeded (%zu bytes)", smem);
-  if (!cache->attr_set) {
-    FFC_CUDA(cudaFuncSetAttribute(ffc_head_sweep_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FFC_CUDA(cudaFuncSetAttribute(ffc_head_sweep_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cache->attr_set = true;
-  }
   const int row_tiles = (a.n_rows + BM - 1) / BM;
   const int n_items = row_tiles * a.n_chunks;
-  dim3 grid(2 * n_items), block(NTHREADS);
-  if (a.sv)
-    ffc_head_sweep_sm100_kernel<true><<<grid, block, smem, s>>>(mp, mw1, mw2, p);
-  else
-    ffc_head_sweep_sm100_kernel<false><<<grid, block, smem, s>>>(mp, mw1, mw2, p);
-  FFC_LAUNCH_CHECK();
-  return FFC_OK;
+#define FFC_SWEEP_CASE(DV)                                                       \
+  case DV:                                                                       \
+    return a.sv ? launch_one<true, DV>(mp, mw1, mw2, p, n_items, s) : launch_one<false, DV>(mp, mw1, mw2, p, n_items, s);
+  switch (a.D) {
+    FFC_SWEEP_CASE(64)
+    FFC_SWEEP_CASE(128)
+    FFC_SWEEP_CASE(256)
+    FFC_SWEEP_CASE(512)
+  }
+#undef FFC_SWEEP_CASE
+  return FFC_ERR_INVALID;
 }
 
 }  // namespace ffc
