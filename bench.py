@@ -134,12 +134,13 @@ class Clocks:
         self.f.flush()
         rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, reasons, mx = [], set(), None
+        sm, reasons, mx, pw = [], set(), None, []
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
         for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
+                pw.append(float(r[3]))
                 for n, v in zip(names, r[4:8]):
                     if v.strip().lower().startswith('active'):
                         reasons.add(n)
@@ -147,7 +148,7 @@ class Clocks:
                 continue
         if sm:
             sm.sort()
-            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), power_w_max=max(pw) if pw else None)
         return out
 
 

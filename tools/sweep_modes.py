@@ -12,6 +12,8 @@ extra = os.environ.get('SWEEP_BENCH_ARGS', '--steps 12 --warmup 3 --no-cpu').spl
 for m in modes:
     env = dict(os.environ, FFC_SM100_DEBUG=m)
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py')] + extra, env=env, capture_output=True, text=True)
+    if os.environ.get('FFC_SM100_DUMP'):
+        print(r.stderr[-3000:], flush=True)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
         print(f"mode {m:>3}: sweep {d['roofline']['avg_ms']:.3f} ms  {d['roofline']['achieved']:.0f} TF  step {d['ms_per_step']:.3f} ms  "

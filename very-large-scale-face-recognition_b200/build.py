@@ -14,6 +14,8 @@ OBJ_DIR = os.path.join(HERE, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr', '-I', os.path.join(HERE, '..', 'include')]
+if os.environ.get('FFC_SM100_DEBUG_BUILD') == '1':      # bottleneck-isolation switches of the sweep (tools/sweep_modes.py); never shipped
+    FLAGS.append('-DFFC_SM100_DEBUG_BUILD=1')
 
 
 def _sources():

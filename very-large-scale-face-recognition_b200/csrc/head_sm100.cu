@@ -18,6 +18,7 @@
 // Synchronisation is all mbarriers: TMA -> MMA (full/empty rings), MMA -> epilogue (tcgen05.commit),
 // epilogue -> peer MMA (st.async complete_tx on the peer's mbarrier), peer MMA -> epilogue (multicast tcgen05.commit).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -59,11 +60,12 @@ struct Bars {   // all in the first 1024 bytes
   uint64_t pt_empty[NPB];          // S-CTA side: P~ buffer b may be overwritten (signalled by the peer's tcgen05.commit)
   uint64_t w2_full[8], w2_empty[8];
   uint64_t pt_full[NPB];           // O-CTA side: P~ buffer b is complete (st.async complete_tx, 32 KB per tile)
+  uint64_t pt_ready[NPB];          // O-CTA side: ... and the proxy fence that lets tcgen05.mma read it has been executed
   uint64_t o_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
-static_assert(sizeof(Bars) <= 512, "barrier block too large");
+static_assert(sizeof(Bars) <= 1024, "barrier block too large");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -245,6 +247,40 @@ __device__ __forceinline__ bool elect_one() {
 #define FFC_SM100_DEBUG_BUILD 0     // 1: honour Sm100Params::debug (bottleneck isolation, see tools/sweep_modes.py)
 #endif
 
+#if FFC_SM100_DEBUG_BUILD
+// per-CTA phase stamps of the last launch: [cta][0..5] = clock64 at start / set-up done / MMA loop start / MMA loop end /
+// role work done / after the final cluster sync; [6], [7] = globaltimer (ns) at start / end
+__device__ long long g_sweep_stamps[1024][8];
+#define FFC_STAMP(slot)                                                                    \
+  do {                                                                                     \
+    if (blockIdx.x < 1024) g_sweep_stamps[blockIdx.x][slot] = clock64();                   \
+  } while (0)
+#define FFC_STAMP_NS(slot)                                                                 \
+  do {                                                                                     \
+    long long t_;                                                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+    if (blockIdx.x < 1024) g_sweep_stamps[blockIdx.x][slot] = t_;                          \
+  } while (0)
+// per-CTA cycle sums: [0] MMA warp waiting for its accumulator / P~ buffer, [1] MMA warp waiting for W (TMA), [2] MMA warp
+// issuing, [3] epilogue warp 4 waiting for S, [4] epilogue warp 4 waiting for a free P~ buffer, [5] epilogue warp 4 working,
+// [6] TMA producer waiting for a free stage
+__device__ long long g_sweep_prof[1024][8];
+#define FFC_PROF_DECL(name) long long name = 0
+#define FFC_PROF_T(var) const long long var = clock64()
+#define FFC_PROF_ADD(acc, t0, t1) acc += (t1) - (t0)
+#define FFC_PROF_STORE(slot, acc)                                                          \
+  do {                                                                                     \
+    if (blockIdx.x < 1024) g_sweep_prof[blockIdx.x][slot] = (acc);                         \
+  } while (0)
+#else
+#define FFC_PROF_DECL(name) do {} while (0)
+#define FFC_PROF_T(var) do {} while (0)
+#define FFC_PROF_ADD(acc, t0, t1) do {} while (0)
+#define FFC_PROF_STORE(slot, acc) do {} while (0)
+#define FFC_STAMP(slot) do {} while (0)
+#define FFC_STAMP_NS(slot) do {} while (0)
+#endif
+
 struct Sm100Params {
   int n_rows;
   int64_t n_cols;
@@ -304,6 +340,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   const int dbg = FFC_SM100_DEBUG_BUILD ? prm.debug : 0;
   const bool dbg_noO = (dbg & 1) != 0, dbg_noEpi = (dbg & 2) != 0, dbg_noS = (dbg & 4) != 0, dbg_noHand = (dbg & 16) != 0, dbg_noTma = (dbg & 64) != 0;
 
+  if (threadIdx.x == 0) {
+    FFC_STAMP(0);
+    FFC_STAMP_NS(6);
+  }
   unsigned char* sP = smem + OFF_DATA;                         // S-CTA
   unsigned char* sW1 = sP + NKC * CHUNK1_BYTES;                // S-CTA
   unsigned char* sPt = smem + OFF_DATA;                        // O-CTA
@@ -322,6 +362,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     for (int i = 0; i < NPB; ++i) {
       mbar_init(&bars.pt_empty[i], 1);
       mbar_init(&bars.pt_full[i], 1);
+      mbar_init(&bars.pt_ready[i], 1);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bars.w2_full[i], 1);
@@ -341,6 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars.tmem_base);
+  if (threadIdx.x == 0) FFC_STAMP(1);
   if (rank == 0) {
     // =========================================== S-CTA ===========================================
     if (warp == 0) {
@@ -354,10 +396,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         __syncwarp();
         int stage = 0;
         uint32_t ph = 0;
+        FFC_PROF_DECL(prof_tma);
         for (int t = t_begin; t < t_end && !dbg_noTma; ++t) {
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
+            FFC_PROF_T(q0);
             mbar_wait(&bars.w_empty[stage], ph ^ 1);
+            FFC_PROF_T(q1);
+            FFC_PROF_ADD(prof_tma, q0, q1);
             if (elect_one()) {
               mbar_expect_tx(&bars.w_full[stage], CHUNK1_BYTES);
               tma_load_2d(&map_w1, &bars.w_full[stage], sW1 + stage * CHUNK1_BYTES, kc * KC, t * BN);
@@ -369,6 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             }
           }
         }
+        if (lane == 0) FFC_PROF_STORE(6, prof_tma);
       }
     } else if (warp == 1) {
       // ---- GEMM-1 issue: S[128 x 128] = P[128 x D] . W_tile[128 x D]^T, 4 x (K = 16) per 64-column chunk ----
@@ -380,10 +427,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const uint64_t b0 = make_desc(smem_u32(sW1), 16, 1024);
         int stage = 0;
         uint32_t ph = 0;
+        if (lane == 0) FFC_STAMP(2);
+        FFC_PROF_DECL(prof_a);
+        FFC_PROF_DECL(prof_b);
+        FFC_PROF_DECL(prof_c);
         for (int i = 0; i < n_tiles; ++i) {
           const int sb = i & (NSB - 1);
+          FFC_PROF_T(q0);
           mbar_wait(&bars.s_empty[sb], ((uint32_t)(i / NSB) & 1) ^ 1);
           tc_fence_after();
+          FFC_PROF_T(q1);
+          FFC_PROF_ADD(prof_a, q0, q1);
           if (dbg_noS) {
             if (elect_one()) mbar_arrive(&bars.s_full[sb]);
             __syncwarp();
@@ -392,10 +446,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           const uint32_t tmem_s = tmem_base + (uint32_t)(sb * BN);
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
+            FFC_PROF_T(q2);
             if (!dbg_noTma) {
               mbar_wait(&bars.w_full[stage], ph);
               tc_fence_after();
             }
+            FFC_PROF_T(q3);
+            FFC_PROF_ADD(prof_b, q2, q3);
             if (elect_one()) {
               const uint64_t ad = a0 + (uint64_t)(kc * (CHUNK1_BYTES >> 4));
               const uint64_t bd = b0 + (uint64_t)(stage * (CHUNK1_BYTES >> 4));
@@ -405,11 +462,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               if (kc == NKC - 1) tc_commit(&bars.s_full[sb]);
             }
             __syncwarp();
+            FFC_PROF_T(q4);
+            FFC_PROF_ADD(prof_c, q3, q4);
             if (++stage == NS1) {
               stage = 0;
               ph ^= 1;
             }
           }
+        }
+        if (lane == 0) {
+          FFC_STAMP(3);
+          FFC_PROF_STORE(0, prof_a);
+          FFC_PROF_STORE(1, prof_b);
+          FFC_PROF_STORE(2, prof_c);
         }
       }
     } else if (warp >= 4) {
@@ -444,15 +509,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       static_assert(NEPI == NPB, "epilogue warpgroups and P~ buffers are paired");
       const int pb = g;
       uint32_t pt_use = 0;
+      FFC_PROF_DECL(prof_e0);
+      FFC_PROF_DECL(prof_e1);
+      FFC_PROF_DECL(prof_e2);
       for (int i = g; i < n_tiles; i += NEPI, ++pt_use) {
         const int sb = i & (NSB - 1);
         const int j0 = (t_begin + i) * BN;
         // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
         uint4 cm = make_uint4(0u, 0u, 0u, 0u);
         if (prm.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(prm.cmask + (j0 >> 5)));
+        FFC_PROF_T(e0);
         mbar_wait(&bars.s_full[sb], (uint32_t)(i / NSB) & 1);
         tc_fence_after();
+        FFC_PROF_T(e1);
         if (!dbg_noHand) mbar_wait(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
+        FFC_PROF_T(e2);
+        FFC_PROF_ADD(prof_e0, e0, e1);
+        FFC_PROF_ADD(prof_e1, e1, e2);
         const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
         const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
         const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
@@ -590,6 +663,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
+        FFC_PROF_T(e3);
+        FFC_PROF_ADD(prof_e2, e2, e3);
+      }
+      if (warp == 4 && lane == 0) {
+        FFC_PROF_STORE(3, prof_e0);
+        FFC_PROF_STORE(4, prof_e1);
+        FFC_PROF_STORE(5, prof_e2);
       }
       // ---- per-row partials: combine the three warpgroups through shared memory ----
       float* stage_v = reinterpret_cast<float*>(sW1);                             // [2][128][KMAX] (W ring is idle now)
@@ -654,10 +734,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       if (n_tiles > 0 && !dbg_noO && !dbg_noTma) {
         int stage = 0;
         uint32_t ph = 0;
+        FFC_PROF_DECL(prof_tma);
         for (int t = t_begin; t < t_end; ++t) {
 #pragma unroll
           for (int jb = 0; jb < BN / JB; ++jb) {
+            FFC_PROF_T(q0);
             mbar_wait(&bars.w2_empty[stage], ph ^ 1);
+            FFC_PROF_T(q1);
+            FFC_PROF_ADD(prof_tma, q0, q1);
             if (elect_one()) {
               mbar_expect_tx(&bars.w2_full[stage], (uint32_t)Sh::STAGE2_BYTES);
               tma_load_3d(&map_w2, &bars.w2_full[stage], sW2 + stage * Sh::STAGE2_BYTES, 0, t * BN + jb * JB, 0);
@@ -669,6 +753,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             }
           }
         }
+        if (lane == 0) FFC_PROF_STORE(6, prof_tma);
       }
     } else if (warp == 1) {
       // ---- GEMM-2 issue: O[128 x D] += P~[128 x 128] . W_tile[128 x D]; per K = 16 queue rows one MMA per 256 features ----
@@ -680,15 +765,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const uint64_t b0 = make_desc(smem_u32(sW2), JB * 128, 1024);
         int stage = 0, pb = 0;
         uint32_t ph = 0, pt_ph = 0;
+        if (lane == 0) FFC_STAMP(2);
+        FFC_PROF_DECL(prof_a);
+        FFC_PROF_DECL(prof_b);
+        FFC_PROF_DECL(prof_c);
         for (int i = 0; i < n_tiles; ++i) {
-          if (!dbg_noHand) {
-            // this lane is the single arriver of pt_full[pb]; the 32 KB of P~ arrive as st.async complete_tx bytes
-            if (elect_one()) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);
-            __syncwarp();
-            mbar_wait_cluster(&bars.pt_full[pb], pt_ph);
-          }
-          asm volatile("fence.proxy.async;" ::: "memory");
+          FFC_PROF_T(q0);
+          if (!dbg_noHand) mbar_wait(&bars.pt_ready[pb], pt_ph);     // P~ complete and fenced by the hand-off warp
           tc_fence_after();
+          FFC_PROF_T(q1);
+          FFC_PROF_ADD(prof_a, q0, q1);
           if (dbg_noO) {
             if (!dbg_noHand && elect_one()) mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb]), 0));
             __syncwarp();
@@ -696,10 +782,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             const uint64_t ap = a0 + (uint64_t)(pb * (PT_BYTES >> 4));
 #pragma unroll
             for (int jb = 0; jb < BN / JB; ++jb) {
+              FFC_PROF_T(q2);
               if (!dbg_noTma) {
                 mbar_wait(&bars.w2_full[stage], ph);
                 tc_fence_after();
               }
+              FFC_PROF_T(q3);
+              FFC_PROF_ADD(prof_b, q2, q3);
               if (elect_one()) {
                 const uint64_t bs = b0 + (uint64_t)(stage * (Sh::STAGE2_BYTES >> 4));
 #pragma unroll
@@ -717,6 +806,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                 if (jb == BN / JB - 1 && !dbg_noHand) tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);
               }
               __syncwarp();
+              FFC_PROF_T(q4);
+              FFC_PROF_ADD(prof_c, q3, q4);
               if (++stage == Sh::NS2) {
                 stage = 0;
                 ph ^= 1;
@@ -732,10 +823,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           if (dbg_noO) mbar_arrive(&bars.o_full); else tc_commit(&bars.o_full);
         }
         __syncwarp();
+        if (lane == 0) {
+          FFC_STAMP(3);
+          FFC_PROF_STORE(0, prof_a);
+          FFC_PROF_STORE(1, prof_b);
+          FFC_PROF_STORE(2, prof_c);
+        }
         mbar_wait(&bars.o_full, 0);     // one polling warp; the 8 epilogue warps block on a hardware barrier instead
       }
       __syncwarp();
       asm volatile("bar.sync 2, 288;" ::: "memory");
+    } else if (warp == 3) {
+      // ---- P~ hand-off: wait for the peer's 32 KB (st.async complete_tx bytes), make the generic-proxy writes visible to the
+      // async proxy (tcgen05.mma reads P~ through it) and pass the buffer on.  The fence costs 200-1100 cycles while TMA
+      // loads are in flight, so it lives here and not in the MMA warp.
+      if (n_tiles > 0 && !dbg_noHand) {
+        int pb = 0;
+        uint32_t pt_ph = 0;
+        for (int i = 0; i < n_tiles; ++i) {
+          if (elect_one()) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);     // the single arriver of pt_full[pb]
+          __syncwarp();
+          mbar_wait_cluster(&bars.pt_full[pb], pt_ph);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __syncwarp();
+          if (elect_one()) mbar_arrive(&bars.pt_ready[pb]);
+          __syncwarp();
+          if (++pb == NPB) {
+            pb = 0;
+            pt_ph ^= 1;
+          }
+        }
+      }
     } else if (warp >= 4 && warp < 12) {
       // ---- O epilogue: TMEM -> global partial [chunk][row][D]; warpgroup g takes half of the columns ----
       const int g = (warp - 4) >> 2;
@@ -779,10 +897,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) FFC_STAMP(4);
   cluster_sync_all();     // the peer may still signal into this CTA's shared memory until here
   if (warp == 2) {
     const uint32_t ncols = rank == 0 ? (uint32_t)(NSB * BN) : (uint32_t)(D < 32 ? 32 : D);
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    FFC_STAMP(5);
+    FFC_STAMP_NS(7);
   }
 }
 
@@ -884,6 +1007,56 @@ static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUten
   }
   kern<<<dim3(2 * n_items), dim3(NTHREADS), smem, s>>>(mp, mw1, mw2, p);
   FFC_LAUNCH_CHECK();
+#if FFC_SM100_DEBUG_BUILD
+  static int dumps_left = getenv("FFC_SM100_DUMP") ? atoi(getenv("FFC_SM100_DUMP")) : 0;
+  static bool said = false;
+  if (!said) {
+    said = true;
+    fprintf(stderr, "[sweep debug build] FFC_SM100_DUMP=%s dumps_left=%d n_items=%d debug=%d\n", getenv("FFC_SM100_DUMP") ? getenv("FFC_SM100_DUMP") : "(null)",
+            dumps_left, n_items, p.debug);
+  }
+  if (dumps_left > 0 && n_items >= 64) {
+    --dumps_left;
+    cudaStreamSynchronize(s);
+    FILE* fo = fopen(getenv("FFC_SM100_DUMP_FILE") ? getenv("FFC_SM100_DUMP_FILE") : "gpurun_out/sweep_stamps.log", "a");
+    if (!fo) fo = stderr;
+    static long long h[1024][8];
+    cudaMemcpyFromSymbol(h, g_sweep_stamps, sizeof(h));
+    const int n = std::min(2 * n_items, 1024);
+    long long t0 = h[0][6], t1 = 0;
+    for (int i = 0; i < n; ++i) {
+      t0 = std::min(t0, h[i][6]);
+      t1 = std::max(t1, h[i][7]);
+    }
+    fprintf(fo, "[sweep stamps] debug=%d %d CTAs, kernel %.1f us (globaltimer)\n", p.debug, 2 * n_items, (t1 - t0) * 1e-3);
+    for (int role = 0; role < 2; ++role) {
+      double acc[5] = {0, 0, 0, 0, 0};
+      int cnt = 0;
+      for (int i = role; i < n; i += 2, ++cnt)
+        for (int k = 0; k < 5; ++k) acc[k] += (double)(h[i][k + 1] - h[i][k]);
+      fprintf(fo, "  %s-CTA avg cycles: setup %.0f | to MMA start %.0f | MMA loop %.0f | drain/epilogue %.0f | final sync %.0f\n", role ? "O" : "S",
+              acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt);
+    }
+    static long long hp[1024][8];
+    cudaMemcpyFromSymbol(hp, g_sweep_prof, sizeof(hp));
+    for (int role = 0; role < 2; ++role) {
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+      int cnt = 0;
+      for (int i = role; i < n; i += 2, ++cnt)
+        for (int k = 0; k < 7; ++k) acc[k] += (double)hp[i][k];
+      const double nt = (double)p.tiles_per_chunk;
+      fprintf(fo, "  %s-CTA cycles/tile: MMA warp waits for %s %.0f, waits for W %.0f, issues %.0f | TMA producer waits %.0f", role ? "O" : "S",
+              role ? "P~" : "a free S buffer", acc[0] / cnt / nt, acc[1] / cnt / nt, acc[2] / cnt / nt, acc[6] / cnt / nt);
+      if (role == 0)
+        fprintf(fo, " | epilogue warp (1 of 3 warpgroups; per tile of the CTA): waits for S %.0f, waits for a free P~ buffer %.0f, works %.0f", acc[3] / cnt / nt,
+                acc[4] / cnt / nt, acc[5] / cnt / nt);
+      fprintf(fo, "\n");
+    }
+    for (int i = 0; i < n; i += 37)
+      fprintf(fo, "  cta %4d: start +%.1f us, end +%.1f us\n", i, (h[i][6] - t0) * 1e-3, (h[i][7] - t0) * 1e-3);
+    if (fo != stderr) fclose(fo);
+  }
+#endif
   return FFC_OK;
 }
 
