@@ -44,6 +44,14 @@ def peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src='fallback')
 
 
+def sweep_traffic(w, world):
+    """DRAM bytes of one main-sweep launch from the committed ncu --set full capture (C3 at one GPU only)."""
+    p = os.path.join(ROOT, 'profiles', 'r1_sweep_traffic.json')
+    if world == 1 and w is WORKLOADS['c3'] and os.path.isfile(p):
+        return json.load(open(p))['dram_bytes_per_launch']
+    return None
+
+
 def make_batches(w, n_batches, seed, rank=0, world=1):
     """id half = chunks of a seeded permutation (same ids in x and y), instance halves iid uniform."""
     import torch
@@ -268,7 +276,7 @@ def run_ours(args, w):
                     e2e=dict(value=samples / (ms_e2e * 1e-3), unit='samples/s', h2d_bytes_per_step=2 * B * D * 4 + 2 * B * 8, d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(launches),
-                    roofline=dict(bound='tensor', achieved=ach, peak=pk['sustained'], unit='TFLOP/s', frac=ach / pk['sustained'], traffic=None,
+                    roofline=dict(bound='tensor', achieved=ach, peak=pk['sustained'], unit='TFLOP/s', frac=ach / pk['sustained'], traffic=sweep_traffic(w, world),
                                   kernel='ffc_head_sweep_sm100_kernel (main sweep)', launches=int(sweep_n), avg_ms=sweep_ms / max(1, sweep_n),
                                   algorithmic_flops_per_launch=flops, peak_kind=f'bf16_tflops_sustained ({pk["src"]})',
                                   frac_of_burst=ach / pk['burst'], sweep_share_of_step=sweep_ms / ms),
