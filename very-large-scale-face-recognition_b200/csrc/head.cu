@@ -351,6 +351,64 @@ __global__ void __launch_bounds__(128) head_reduce_kernel(const float* __restric
   }
 }
 
+// The same reduction for up to three sweeps in one launch (blockIdx.y = sweep): the merged main + side launch of the bf16 path.
+struct ReduceJob {
+  const float* l_part;
+  const float* o_part;
+  const float* topv_part;
+  const int32_t* topi_part;
+  int n_chunks;
+  float* lsum;
+  float* osum;
+  float* topv;
+  int32_t* topi;
+  int64_t idx_base;
+  const int32_t* idx_map;
+};
+struct ReduceJobs {
+  ReduceJob j[3];
+};
+__global__ void __launch_bounds__(128) head_reduce_multi_kernel(const ReduceJobs jobs, int n_rows, int D, int k, const uint8_t* __restrict__ is_out) {
+  const ReduceJob& r = jobs.j[blockIdx.y];
+  const int i = blockIdx.x;
+  const int n_chunks = r.n_chunks;
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < n_chunks; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(r.o_part + ((int64_t)c * n_rows + i) * D + d);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(r.osum + (int64_t)i * D + d) = acc;
+  }
+  if (threadIdx.x == 96) {      // scalar part (denominator, top-k merge) on one lane of the last warp
+    float acc = 0.f;
+    for (int c = 0; c < n_chunks; ++c) acc += r.l_part[(int64_t)c * n_rows + i];
+    r.lsum[i] = acc;
+    float tv[KMAX];
+    int32_t ti[KMAX];
+    for (int q = 0; q < KMAX; ++q) {
+      tv[q] = -INFINITY;
+      ti[q] = -1;
+    }
+    if (is_out[i]) {
+      for (int c = 0; c < n_chunks; ++c)
+        for (int q = 0; q < k; ++q) {
+          const float v = r.topv_part[((int64_t)c * n_rows + i) * k + q];
+          if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, r.topi_part[((int64_t)c * n_rows + i) * k + q]);
+        }
+    }
+    for (int q = 0; q < k; ++q) {
+      r.topv[(int64_t)i * k + q] = tv[q];
+      int32_t id = ti[q];
+      if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
+      r.topi[(int64_t)i * k + q] = id;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // finalize
 // ------------------------------------------------------------------------------------------------
@@ -541,7 +599,7 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
   const int64_t R = cfg->max_rows, D = cfg->feat_dim;
-  h->part_rows_cap = std::max<int64_t>(16 * R, 40960);
+  h->part_rows_cap = std::max<int64_t>(20 * R, 40960);
   h->max_chunks = 1024;
   FFC_CUDA(cudaMalloc(&h->p16, R * D * sizeof(__nv_bfloat16)));
   FFC_CUDA(cudaMalloc(&h->side_f32, 2 * R * D * sizeof(float)));
@@ -629,6 +687,76 @@ static int run_one_sweep(ffc_head* h, SweepArgs a, int cache_slot, int stat_slot
   return FFC_OK;
 }
 
+// bf16, AM / Arc: the main sweep over queue[0] and the two side sweeps over the gathered `ones` rows of queue[0] / queue[1] as ONE
+// launch of the tcgen05 kernel (their items are concatenated), followed by one reduce launch.
+static int run_merged_sweeps(ffc_head* h, SweepArgs a, const ffc_head_pass* in, const ffc_head_stats* out, cudaStream_t s) {
+  const ffc_head_config& c = h->cfg;
+  const int n = a.n_rows, D = a.D, k = a.k;
+  SweepArgs sw[3];
+  ReduceJobs jobs;
+  int64_t part_row = 0;
+  for (int i = 0; i < 3; ++i) {
+    SweepArgs& w = sw[i];
+    w = a;
+    if (i == 0) {
+      w.W_bf16 = (const __nv_bfloat16*)in->queue_bf16;
+      w.n_cols = c.q_local;
+      w.n_cols_dev = nullptr;
+      w.tcol = h->tcol;
+      w.cmask = in->cmask;
+      w.n_chunks = sm100_pick_chunks(n, w.n_cols, D);
+    } else {
+      w.W_bf16 = h->side_bf16 + (int64_t)(i - 1) * c.max_rows * D;
+      w.n_cols = c.max_rows;
+      w.n_cols_dev = in->n_ones;
+      w.tcol = h->tpos;
+      w.cmask = nullptr;
+      w.n_chunks = 1;
+    }
+    w.thr = nullptr;
+    w.l_part = h->l_part + part_row;
+    w.o_part = h->o_part + part_row * D;
+    w.topv_part = h->topv_part + part_row * k;
+    w.topi_part = h->topi_part + part_row * k;
+    const int stat_slot = i == 0 ? 0 : 1 + i, top_slot = i;
+    ReduceJob& r = jobs.j[i];
+    r.l_part = w.l_part;
+    r.o_part = w.o_part;
+    r.topv_part = w.topv_part;
+    r.topi_part = w.topi_part;
+    r.n_chunks = w.n_chunks;
+    r.lsum = out->lsum + (int64_t)stat_slot * n;
+    r.osum = out->osum + (int64_t)stat_slot * n * D;
+    r.topv = out->topv + (int64_t)top_slot * n * k;
+    r.topi = out->topi + (int64_t)top_slot * n * k;
+    r.idx_base = c.col_offset;
+    r.idx_map = i == 0 ? nullptr : in->ones_list;
+    part_row += (int64_t)w.n_chunks * n;
+  }
+  FFC_REQUIRE(part_row <= h->part_rows_cap && sw[0].n_chunks <= h->max_chunks, "head sweep: partial workspace too small (%d chunks x %d rows)",
+              sw[0].n_chunks, n);
+  const bool timed = h->timing != 0;
+  if (timed) {
+    if (h->ev_used + 2 > h->ev->size()) {
+      for (int e = 0; e < 2; ++e) {
+        cudaEvent_t ev;
+        FFC_CUDA(cudaEventCreate(&ev));
+        h->ev->push_back(ev);
+      }
+    }
+    FFC_CUDA(cudaEventRecord((*h->ev)[h->ev_used], s));
+  }
+  int rc = launch_sweeps_sm100(h->sm100, sw, 3, s);
+  if (rc) return rc;
+  if (timed) {
+    FFC_CUDA(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
+    h->ev_used += 2;
+  }
+  head_reduce_multi_kernel<<<dim3(n, 3), 128, 0, s>>>(jobs, n, D, k, a.is_out);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
 extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
   FFC_REQUIRE(h && in && out, "ffc_head_sweep: NULL argument");
   const ffc_head_config& c = h->cfg;
@@ -672,6 +800,7 @@ extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   a.sv = sv;
   a.k = c.topk;
   int rc;
+  if (bf16 && !sv) return run_merged_sweeps(h, a, in, out, s);
   // main sweep(s) over queue[0]: everything except the target column and the `ones` columns
   a.W_f32 = qf;
   a.W_bf16 = qh;

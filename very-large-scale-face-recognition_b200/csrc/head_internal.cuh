@@ -43,6 +43,8 @@ struct Sm100Cache;
 Sm100Cache* sm100_cache_create();
 void sm100_cache_destroy(Sm100Cache*);
 int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cudaStream_t s);
+// up to three sweeps that share the probe rows in ONE launch (main + the two side sweeps)
+int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps, cudaStream_t s);
 int sm100_pick_chunks(int n_rows, int64_t n_cols, int D);
 
 // sorted (descending) insertion into a k-entry list held in registers / local arrays

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <vector>
@@ -281,24 +282,32 @@ __device__ long long g_sweep_prof[1024][8];
 #define FFC_STAMP_NS(slot) do {} while (0)
 #endif
 
-struct Sm100Params {
-  int n_rows;
+// One launch runs up to MAX_SUB sweeps that share the probe rows P (their work items are concatenated): the main sweep over
+// queue[0] and the two tiny side sweeps over the gathered `ones` rows.  The main sweep of C3 fills 72 of the 74 CTA-pair
+// slots, so the side items run on the two spare pairs while it is in flight instead of as two more launches.
+constexpr int MAX_SUB = 3;
+struct SubSweep {
   int64_t n_cols;
   const int32_t* n_cols_dev;
   const int32_t* tcol;
   const uint32_t* cmask;
   const float* thr;
-  const uint8_t* is_out;
-  float a2, b2;       // p~ = 2^(a2 * z - b2)
-  int k;
-  int n_chunks, tiles_per_chunk;
-  int debug;   // bottleneck isolation BITMASK, only in FFC_SM100_DEBUG_BUILD builds; results are WRONG when any bit is set:
-               // 1 = O-CTA skips TMA+MMA, 2 = epilogue skips tcgen05.ld/exp, 4 = S-CTA skips TMA+MMA,
-               // 16 = no P~ hand-off (both CTAs free-run), 64 = no W TMA loads (MMAs run on whatever is in shared memory)
+  int tiles_per_chunk;
+  int item0;          // first work item of this sweep (items are [row tile fastest][column chunk])
   float* l_part;
   float* o_part;
   float* topv_part;
   int32_t* topi_part;
+};
+struct Sm100Params {
+  int n_rows;
+  const uint8_t* is_out;
+  float a2, b2;       // p~ = 2^(a2 * z - b2)
+  int k;
+  int debug;   // bottleneck isolation BITMASK, only in FFC_SM100_DEBUG_BUILD builds; results are WRONG when any bit is set:
+               // 1 = O-CTA skips TMA+MMA, 2 = epilogue skips tcgen05.ld/exp, 4 = S-CTA skips TMA+MMA,
+               // 16 = no P~ hand-off (both CTAs free-run), 64 = no W TMA loads (MMAs run on whatever is in shared memory)
+  SubSweep sub[MAX_SUB];
 };
 
 template <int D>
@@ -317,8 +326,10 @@ struct SweepShape {
 
 template <bool SV, int D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-    ffc_head_sweep_sm100_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_w1,
-                                const __grid_constant__ CUtensorMap map_w2, const Sm100Params prm) {
+    ffc_head_sweep_sm100_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_w1a,
+                                const __grid_constant__ CUtensorMap map_w2a, const __grid_constant__ CUtensorMap map_w1b,
+                                const __grid_constant__ CUtensorMap map_w2b, const __grid_constant__ CUtensorMap map_w1c,
+                                const __grid_constant__ CUtensorMap map_w2c, const __grid_constant__ Sm100Params prm) {
   using Sh = SweepShape<D>;
   constexpr int NKC = Sh::NKC;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -327,14 +338,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   Bars& bars = *reinterpret_cast<Bars*>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int item = blockIdx.x >> 1;
+  const int item_all = blockIdx.x >> 1;
+  const int sidx = item_all >= prm.sub[2].item0 ? 2 : (item_all >= prm.sub[1].item0 ? 1 : 0);
+  const SubSweep& sw = prm.sub[sidx];
+  const CUtensorMap* map_w1 = sidx == 0 ? &map_w1a : (sidx == 1 ? &map_w1b : &map_w1c);
+  const CUtensorMap* map_w2 = sidx == 0 ? &map_w2a : (sidx == 1 ? &map_w2b : &map_w2c);
+  const int item = item_all - sw.item0;
   const int n_row_tiles = (prm.n_rows + BM - 1) / BM;
   const int rt = item % n_row_tiles, chunk = item / n_row_tiles;
   const int row0 = rt * BM;
-  const int64_t n_cols = prm.n_cols_dev ? (int64_t)*prm.n_cols_dev : prm.n_cols;
+  const int64_t n_cols = sw.n_cols_dev ? (int64_t)*sw.n_cols_dev : sw.n_cols;
   const int n_tiles_total = (int)((n_cols + BN - 1) / BN);
-  const int t_begin = chunk * prm.tiles_per_chunk;
-  int t_end = t_begin + prm.tiles_per_chunk;
+  const int t_begin = chunk * sw.tiles_per_chunk;
+  int t_end = t_begin + sw.tiles_per_chunk;
   if (t_end > n_tiles_total) t_end = n_tiles_total;
   const int n_tiles = t_end > t_begin ? t_end - t_begin : 0;
   const int dbg = FFC_SM100_DEBUG_BUILD ? prm.debug : 0;
@@ -406,7 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             FFC_PROF_ADD(prof_tma, q0, q1);
             if (elect_one()) {
               mbar_expect_tx(&bars.w_full[stage], CHUNK1_BYTES);
-              tma_load_2d(&map_w1, &bars.w_full[stage], sW1 + stage * CHUNK1_BYTES, kc * KC, t * BN);
+              tma_load_2d(map_w1, &bars.w_full[stage], sW1 + stage * CHUNK1_BYTES, kc * KC, t * BN);
             }
             __syncwarp();
             if (++stage == NS1) {
@@ -484,11 +500,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const int r_local = q4 * 32 + lane;         // row within the item
       const int row = row0 + r_local;
       const bool row_ok = row < prm.n_rows;
-      const int32_t tcol = row_ok ? prm.tcol[row] : -1;
+      const int32_t tcol = row_ok ? sw.tcol[row] : -1;
       const bool outl = row_ok && prm.is_out[row];
       const bool warp_out = __any_sync(0xffffffffu, outl);
       float thr = INFINITY;
-      if (SV && row_ok && prm.thr) thr = prm.thr[row];
+      if (SV && row_ok && sw.thr) thr = sw.thr[row];
       const float a2 = prm.a2, b2 = prm.b2;
       const int k = prm.k;
       float lsum = 0.f;
@@ -517,7 +533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const int j0 = (t_begin + i) * BN;
         // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
         uint4 cm = make_uint4(0u, 0u, 0u, 0u);
-        if (prm.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(prm.cmask + (j0 >> 5)));
+        if (sw.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(sw.cmask + (j0 >> 5)));
         FFC_PROF_T(e0);
         mbar_wait(&bars.s_full[sb], (uint32_t)(i / NSB) & 1);
         tc_fence_after();
@@ -717,12 +733,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           }
         }
         const int64_t pr = (int64_t)chunk * prm.n_rows + row;
-        prm.l_part[pr] = lsum;
+        sw.l_part[pr] = lsum;
 #pragma unroll
         for (int q = 0; q < KMAX; ++q) {
           if (q < k) {
-            prm.topv_part[pr * k + q] = tv[q];
-            prm.topi_part[pr * k + q] = ti[q];
+            sw.topv_part[pr * k + q] = tv[q];
+            sw.topi_part[pr * k + q] = ti[q];
           }
         }
       }
@@ -744,7 +760,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             FFC_PROF_ADD(prof_tma, q0, q1);
             if (elect_one()) {
               mbar_expect_tx(&bars.w2_full[stage], (uint32_t)Sh::STAGE2_BYTES);
-              tma_load_3d(&map_w2, &bars.w2_full[stage], sW2 + stage * Sh::STAGE2_BYTES, 0, t * BN + jb * JB, 0);
+              tma_load_3d(map_w2, &bars.w2_full[stage], sW2 + stage * Sh::STAGE2_BYTES, 0, t * BN + jb * JB, 0);
             }
             __syncwarp();
             if (++stage == Sh::NS2) {
@@ -864,7 +880,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       asm volatile("bar.sync 2, 288;" ::: "memory");   // released by the MMA warp once every tcgen05.mma of the item has completed
       tc_fence_after();
       constexpr int half = D / 2;                  // D is a multiple of 64
-      float* dst = prm.o_part + ((int64_t)chunk * prm.n_rows + (row_ok ? row : 0)) * D + g * half;
+      float* dst = sw.o_part + ((int64_t)chunk * prm.n_rows + (row_ok ? row : 0)) * D + g * half;
       for (int c0 = 0; c0 < half; c0 += 32) {
         uint32_t v[32];
         if (n_tiles > 0) {
@@ -889,10 +905,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     const int row = row0 + r_local;
     if (row < prm.n_rows) {
       const int64_t pr = (int64_t)chunk * prm.n_rows + row;
-      prm.l_part[pr] = 0.f;
+      sw.l_part[pr] = 0.f;
       for (int q = 0; q < prm.k; ++q) {
-        prm.topv_part[pr * prm.k + q] = -INFINITY;
-        prm.topi_part[pr * prm.k + q] = -1;
+        sw.topv_part[pr * prm.k + q] = -INFINITY;
+        sw.topi_part[pr * prm.k + q] = -1;
       }
     }
   }
@@ -997,7 +1013,7 @@ int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
 }
 
 template <bool SV, int D>
-static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUtensorMap& mw2, const Sm100Params& p, int n_items, cudaStream_t s) {
+static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items, cudaStream_t s) {
   static bool attr_set = false;
   auto kern = ffc_head_sweep_sm100_kernel<SV, D>;
   constexpr size_t smem = SweepShape<D>::SMEM;
@@ -1005,16 +1021,10 @@ static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUten
     FFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  kern<<<dim3(2 * n_items), dim3(NTHREADS), smem, s>>>(mp, mw1, mw2, p);
+  kern<<<dim3(2 * n_items), dim3(NTHREADS), smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
   FFC_LAUNCH_CHECK();
 #if FFC_SM100_DEBUG_BUILD
   static int dumps_left = getenv("FFC_SM100_DUMP") ? atoi(getenv("FFC_SM100_DUMP")) : 0;
-  static bool said = false;
-  if (!said) {
-    said = true;
-    fprintf(stderr, "[sweep debug build] FFC_SM100_DUMP=%s dumps_left=%d n_items=%d debug=%d\n", getenv("FFC_SM100_DUMP") ? getenv("FFC_SM100_DUMP") : "(null)",
-            dumps_left, n_items, p.debug);
-  }
   if (dumps_left > 0 && n_items >= 64) {
     --dumps_left;
     cudaStreamSynchronize(s);
@@ -1022,21 +1032,13 @@ static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUten
     if (!fo) fo = stderr;
     static long long h[1024][8];
     cudaMemcpyFromSymbol(h, g_sweep_stamps, sizeof(h));
-    const int n = std::min(2 * n_items, 1024);
+    const int n = std::min(2 * std::min(n_items, p.sub[1].item0), 1024);     // main-sweep CTAs only
     long long t0 = h[0][6], t1 = 0;
     for (int i = 0; i < n; ++i) {
       t0 = std::min(t0, h[i][6]);
       t1 = std::max(t1, h[i][7]);
     }
     fprintf(fo, "[sweep stamps] debug=%d %d CTAs, kernel %.1f us (globaltimer)\n", p.debug, 2 * n_items, (t1 - t0) * 1e-3);
-    for (int role = 0; role < 2; ++role) {
-      double acc[5] = {0, 0, 0, 0, 0};
-      int cnt = 0;
-      for (int i = role; i < n; i += 2, ++cnt)
-        for (int k = 0; k < 5; ++k) acc[k] += (double)(h[i][k + 1] - h[i][k]);
-      fprintf(fo, "  %s-CTA avg cycles: setup %.0f | to MMA start %.0f | MMA loop %.0f | drain/epilogue %.0f | final sync %.0f\n", role ? "O" : "S",
-              acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt);
-    }
     static long long hp[1024][8];
     cudaMemcpyFromSymbol(hp, g_sweep_prof, sizeof(hp));
     for (int role = 0; role < 2; ++role) {
@@ -1044,7 +1046,7 @@ static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUten
       int cnt = 0;
       for (int i = role; i < n; i += 2, ++cnt)
         for (int k = 0; k < 7; ++k) acc[k] += (double)hp[i][k];
-      const double nt = (double)p.tiles_per_chunk;
+      const double nt = (double)p.sub[0].tiles_per_chunk;
       fprintf(fo, "  %s-CTA cycles/tile: MMA warp waits for %s %.0f, waits for W %.0f, issues %.0f | TMA producer waits %.0f", role ? "O" : "S",
               role ? "P~" : "a free S buffer", acc[0] / cnt / nt, acc[1] / cnt / nt, acc[2] / cnt / nt, acc[6] / cnt / nt);
       if (role == 0)
@@ -1052,37 +1054,29 @@ static int launch_one(const CUtensorMap& mp, const CUtensorMap& mw1, const CUten
                 acc[4] / cnt / nt, acc[5] / cnt / nt);
       fprintf(fo, "\n");
     }
-    for (int i = 0; i < n; i += 37)
-      fprintf(fo, "  cta %4d: start +%.1f us, end +%.1f us\n", i, (h[i][6] - t0) * 1e-3, (h[i][7] - t0) * 1e-3);
     if (fo != stderr) fclose(fo);
   }
 #endif
   return FFC_OK;
 }
 
-int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cudaStream_t s) {
-  (void)cache_slot;
+// `sweeps[0 .. n_sweeps)` share P, n_rows, D, is_out, scale, fixed_max, sv and k (taken from sweeps[0]); each has its own
+// weight matrix, exclusions, chunk count and partial outputs.
+int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps, cudaStream_t s) {
+  FFC_REQUIRE(n_sweeps >= 1 && n_sweeps <= MAX_SUB, "tcgen05 sweep: %d sweeps per launch (1..%d)", n_sweeps, MAX_SUB);
+  const SweepArgs& a = sweeps[0];
   FFC_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256 || a.D == 512, "tcgen05 sweep: D=%d must be 64, 128, 256 or 512", a.D);
-  FFC_REQUIRE(a.W_bf16 && a.P_bf16, "tcgen05 sweep: bf16 operands missing");
-  CUtensorMap mp, mw1, mw2;
+  FFC_REQUIRE(a.P_bf16, "tcgen05 sweep: bf16 operands missing");
+  CUtensorMap maps[1 + 2 * MAX_SUB];
   int rc;
-  if ((rc = get_map(cache, a.P_bf16, a.n_rows, a.D, BM, false, &mp))) return rc;
-  if ((rc = get_map(cache, a.W_bf16, a.n_cols, a.D, BN, false, &mw1))) return rc;
-  if ((rc = get_map(cache, a.W_bf16, a.n_cols, a.D, JB, true, &mw2))) return rc;
+  if ((rc = get_map(cache, a.P_bf16, a.n_rows, a.D, BM, false, &maps[0]))) return rc;
   Sm100Params p;
+  memset(&p, 0, sizeof(p));
   p.n_rows = a.n_rows;
-  p.n_cols = a.n_cols;
-  p.n_cols_dev = a.n_cols_dev;
-  p.tcol = a.tcol;
-  p.cmask = a.cmask;
-  p.thr = a.thr;
   p.is_out = a.is_out;
   p.a2 = a.scale * LOG2E;
   p.b2 = a.fixed_max * LOG2E;
   p.k = a.k;
-  p.n_chunks = a.n_chunks;
-  const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(a.n_cols, BN));
-  p.tiles_per_chunk = (int)ceil_div64(n_tiles, a.n_chunks);
   p.debug = 0;
 #if FFC_SM100_DEBUG_BUILD
   {
@@ -1090,15 +1084,38 @@ int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cu
     p.debug = dbg ? atoi(dbg) : 0;
   }
 #endif
-  p.l_part = a.l_part;
-  p.o_part = a.o_part;
-  p.topv_part = a.topv_part;
-  p.topi_part = a.topi_part;
   const int row_tiles = (a.n_rows + BM - 1) / BM;
-  const int n_items = row_tiles * a.n_chunks;
+  int n_items = 0;
+  for (int i = 0; i < MAX_SUB; ++i) {
+    SubSweep& sb = p.sub[i];
+    if (i >= n_sweeps) {       // unused slots: no items, maps duplicated from sweep 0 (never dereferenced)
+      sb.item0 = 0x7fffffff;
+      maps[1 + 2 * i] = maps[1];
+      maps[2 + 2 * i] = maps[2];
+      continue;
+    }
+    const SweepArgs& w = sweeps[i];
+    FFC_REQUIRE(w.W_bf16 && w.n_rows == a.n_rows && w.D == a.D && w.P_bf16 == a.P_bf16 && w.sv == a.sv && w.k == a.k && w.n_chunks >= 1,
+                "tcgen05 sweep: sweep %d does not share the probe rows / shape of sweep 0", i);
+    if ((rc = get_map(cache, w.W_bf16, w.n_cols, w.D, BN, false, &maps[1 + 2 * i]))) return rc;
+    if ((rc = get_map(cache, w.W_bf16, w.n_cols, w.D, JB, true, &maps[2 + 2 * i]))) return rc;
+    sb.n_cols = w.n_cols;
+    sb.n_cols_dev = w.n_cols_dev;
+    sb.tcol = w.tcol;
+    sb.cmask = w.cmask;
+    sb.thr = w.thr;
+    const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(w.n_cols, BN));
+    sb.tiles_per_chunk = (int)ceil_div64(n_tiles, w.n_chunks);
+    sb.item0 = n_items;
+    sb.l_part = w.l_part;
+    sb.o_part = w.o_part;
+    sb.topv_part = w.topv_part;
+    sb.topi_part = w.topi_part;
+    n_items += row_tiles * w.n_chunks;
+  }
 #define FFC_SWEEP_CASE(DV)                                                       \
   case DV:                                                                       \
-    return a.sv ? launch_one<true, DV>(mp, mw1, mw2, p, n_items, s) : launch_one<false, DV>(mp, mw1, mw2, p, n_items, s);
+    return a.sv ? launch_one<true, DV>(maps, p, n_items, s) : launch_one<false, DV>(maps, p, n_items, s);
   switch (a.D) {
     FFC_SWEEP_CASE(64)
     FFC_SWEEP_CASE(128)
@@ -1107,6 +1124,11 @@ int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cu
   }
 #undef FFC_SWEEP_CASE
   return FFC_ERR_INVALID;
+}
+
+int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cudaStream_t s) {
+  (void)cache_slot;
+  return launch_sweeps_sm100(cache, &a, 1, s);
 }
 
 }  // namespace ffc
