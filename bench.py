@@ -184,18 +184,13 @@ def run_ours(args, w):
         head = ffc_b200.FFCHead(D, Q, w['scale'], w['loss_type'], w['margin'], precision='bf16', max_batch=B, device=dev)
         head._ensure()
         # steady state: LRU full: ids 0..Q-1 resident, slot i <- id i, recency = id order
-        head._lru.restore_arrays(torch.arange(Q, dtype=torch.int64), torch.arange(Q, dtype=torch.int32))
+        head.lru.restore_arrays(torch.arange(Q, dtype=torch.int64), torch.arange(Q, dtype=torch.int32))
 
-        def step(x, y, xl, yl):
-            l2, d2 = head._pass(x, y, xl, yl, False)
-            l1, d1 = head._pass(y, x, yl, xl, True)
-            return l1 + l2
+        def step(x, y, xl, yl):          # rollback pass (probe x, gallery y) + commit pass (probe y, gallery x): loss and both dEmb
+            return head.forward_pair(x, y, y, x, xl, yl)[0]
 
-        def step_api(x, y, xl, yl):      # public API, gradients requested
-            x = x.requires_grad_(True)
-            y = y.requires_grad_(True)
-            loss = head.head(x, y.detach(), xl, yl, commit=False) + head.head(y, x.detach(), yl, xl, commit=True)
-            return loss
+        def step_api(x, y, xl, yl):      # public API (FFC.forward with embeddings in), gradients requested
+            return head(x.requires_grad_(True), y.requires_grad_(True), xl, yl)
     else:
         from ffc_b200.dist import ShardedFFCHead
         head = ShardedFFCHead(D, Q, w['scale'], w['loss_type'], w['margin'], max_batch=B, device=dev)

@@ -68,6 +68,22 @@ class _HeadFn(torch.autograd.Function):
         return (dp * grad_out).to(ctx.p_dtype), None, None, None, None, None
 
 
+class _HeadPairFn(torch.autograd.Function):
+    """Both passes of ffc.py:264-267 in one call, so that the commit pass's bookkeeping can run under the rollback sweep."""
+
+    @staticmethod
+    def forward(ctx, p_rb, p_cm, head, g_rb, g_cm, x_label, y_label):
+        loss, d_rb, d_cm = head.forward_pair(p_rb.detach(), g_rb, p_cm.detach(), g_cm, x_label, y_label)
+        ctx.save_for_backward(d_rb, d_cm)
+        ctx.dtypes = (p_rb.dtype, p_cm.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d_rb, d_cm = ctx.saved_tensors
+        return (d_rb * grad_out).to(ctx.dtypes[0]), (d_cm * grad_out).to(ctx.dtypes[1]), None, None, None, None, None
+
+
 class FFCHead(Module):
     """State and kernels of the FFC head: prototype queue [2,Q,D] (+ bf16 mirror), device LRU, queue positions."""
 
@@ -104,8 +120,10 @@ class FFCHead(Module):
             self._lru = LRU(Q, device=dev)
             self.qpos = torch.zeros(Q, dtype=torch.uint8, device=dev)
             self.queue_bf16 = torch.empty(2, Q, D, dtype=torch.bfloat16, device=dev)
-            self.cmask = torch.zeros((Q + 31) // 32 + 1, dtype=torch.int32, device=dev)
             self._alloc_batch(R)
+            # LRU bookkeeping runs on its own stream, ahead of the sweeps of the main stream (see forward_pair)
+            self._side = torch.cuda.Stream(device=dev)
+            self._lru_sync_main = True
             cfg = HeadConfig(R, Q, Q, 0, D, _capi.LOSS_TYPES[self.loss_type], self.scale, self.margin, self.hard_neg,
                              _capi.PRECISIONS[self.precision])
             h = C.c_void_p()
@@ -124,15 +142,21 @@ class FFCHead(Module):
         dev, D, k = self.queue.device, self.feat_dim, self.hard_neg
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        self.rows = torch.empty(R, **i32)
-        self.cols = torch.empty(R, **i32)
-        self.label = torch.empty(R, **i32)
-        self.ones_list = torch.empty(R, **i32)
-        self.n_ones = torch.zeros(1, **i32)
+        Q = self.queue_size
+        # per-pass bookkeeping state, two sets (rollback pass / commit pass): the bookkeeping of a pass may be computed while
+        # the previous pass is still sweeping
+        self._sets = [dict(rows=torch.empty(R, **i32), cols=torch.empty(R, **i32), label=torch.empty(R, **i32), ones_list=torch.empty(R, **i32),
+                           n_ones=torch.zeros(1, **i32), cmask=torch.zeros((Q + 31) // 32 + 1, **i32), free=None) for _ in range(2)]
+        self._use_set(0)
         self.undo_rows = torch.empty(R, D, **f32)
         self.loss_buf = torch.zeros(1, **f32)
         self.stats = dict(lsum=torch.empty(4, R, **f32), osum=torch.empty(4, R, D, **f32), tgt=torch.empty(4, R, **f32),
                           topv=torch.empty(3, R, k, **f32), topi=torch.empty(3, R, k, **i32))
+
+    def _use_set(self, i):
+        st = self._sets[i]
+        self.rows, self.cols, self.label, self.ones_list, self.n_ones, self.cmask = (st[k] for k in ('rows', 'cols', 'label', 'ones_list', 'n_ones', 'cmask'))
+        return st
 
     def __del__(self):
         h = self.__dict__.pop('_h', None)
@@ -146,6 +170,8 @@ class FFCHead(Module):
     def lru(self):
         """The device LRU (reference attribute ``ffc_net.lru``, main.py:85); created on first use."""
         self._ensure()
+        self._side.synchronize()          # bookkeeping enqueued by earlier passes
+        self._lru_sync_main = True        # whatever the caller does with it happens on the caller's stream
         return self._lru
 
     def set_timing(self, enable):
@@ -170,6 +196,7 @@ class FFCHead(Module):
         if self._lru is None:
             src = self._pending_qpos if self._pending_qpos is not None else torch.zeros(self.queue_size, dtype=torch.uint8)
         else:
+            self._side.synchronize()
             src = self.qpos
         return dict(enumerate(src.cpu().tolist()))
 
@@ -179,6 +206,8 @@ class FFCHead(Module):
         if self._lru is None:
             self._pending_qpos = t
         else:
+            self._side.synchronize()
+            self._lru_sync_main = True
             self.qpos.copy_(t.to(self.qpos.device))
 
     def _labels_dev(self, lab, n):
@@ -187,46 +216,106 @@ class FFCHead(Module):
         return t.to(device=self._dev, dtype=torch.int64, non_blocking=True).contiguous()
 
     # -- one head pass ------------------------------------------------------------------------------
-    def _pass(self, p, g, probe_label, gallery_label, commit):
-        self._ensure()
+    def _bookkeep(self, set_idx, gallery_label, probe_label, B, commit, main, labels_on_main):
+        """LRU side of a pass on the bookkeeping stream: ffc.py:162-177 / 214-235 (get / try_get, rows, cols, `ones`), the probe
+        labels (ffc.py:189-194 / 242-246) and, on a rollback pass, the LRU / queue-position undo (ffc.py:256-259) -- the sweep
+        only needs the labels, `ones` and the queue rows, never the LRU.  Returns the event the main stream has to wait for."""
+        side, st = self._side, self._sets[set_idx]
+        if labels_on_main or self._lru_sync_main:
+            ev_in = torch.cuda.Event()
+            ev_in.record(main)
+            side.wait_event(ev_in)
+            self._lru_sync_main = False
+        if st['free'] is not None:
+            side.wait_event(st['free'])           # the pass that used this set last has finished with it
+        with torch.cuda.stream(side):
+            kg = self._labels_dev(gallery_label, B)
+            kp = self._labels_dev(probe_label, B)
+            st['n_ones'].zero_()
+            self._lru.assign(kg, journal=not commit, qpos=self.qpos, rows=st['rows'], cols=st['cols'], ones_list=st['ones_list'],
+                             n_ones=st['n_ones'], cmask=st['cmask'])
+            self._lru.view_batch(kp, st['label'])
+            if not commit:
+                self._lru.undo(B, self.qpos)
+            done = torch.cuda.Event()
+            done.record(side)
+        return done
+
+    def _finish(self, set_idx, p, g, B, commit, main):
+        """Queue and sweep side of a pass on the caller's stream."""
         lib, dev = self._lib, self._dev
         Q, D = self.queue_size, self.feat_dim
-        B = p.shape[0]
+        st = self._use_set(set_idx)
+        p32 = p.to(device=dev, dtype=torch.float32).contiguous()
+        g32 = g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        s = main.cuda_stream
+        # ffc.py:179-182 / 237-241: enqueue (fp32 queue + bf16 mirror), old rows saved on a rollback pass
+        check(lib.ffc_queue_scatter(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                    g32.data_ptr(), B, Q, D, None if commit else self.undo_rows.data_ptr(), s))
+        hp = HeadPass(p32.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.label.data_ptr(),
+                      self.ones_list.data_ptr(), self.n_ones.data_ptr(), self.cmask.data_ptr(), B)
+        hs = HeadStats(*(self._stat_ptr(name, B) for name in ('lsum', 'osum', 'tgt', 'topv', 'topi')))
+        self.loss_buf.zero_()
+        dp = torch.empty(B, D, dtype=torch.float32, device=dev)
+        # ffc.py:195-202 / 248-254 + backward
+        check(lib.ffc_head_sweep(self._h, C.byref(hp), C.byref(hs), s))
+        check(lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), 1, self.loss_buf.data_ptr(), dp.data_ptr(), s))
+        loss = self.loss_buf[0].clone()
+        if not commit:   # ffc.py:255: the queue rows come back; the LRU was undone by the bookkeeping stream
+            check(lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                        self.undo_rows.data_ptr(), B, Q, D, s))
+        self.cmask.zero_()
+        st['free'] = torch.cuda.Event()
+        st['free'].record(main)
+        self._last = dict(rows=self.rows[:B], cols=self.cols[:B], label=self.label[:B], ones=self.ones_list, n_ones=self.n_ones)
+        return loss, dp
+
+    def _check_batch(self, p, g):
+        B, D = p.shape[0], self.feat_dim
         assert p.shape == (B, D) and g.shape == (B, D), (p.shape, g.shape)
         assert 1 <= B <= self.max_batch, f'batch {B} > max_batch {self.max_batch}'
         assert self.queue.is_contiguous()
-        p32 = p.to(device=dev, dtype=torch.float32).contiguous()
-        g32 = g.detach().to(device=dev, dtype=torch.float32).contiguous()
-        kg = self._labels_dev(gallery_label, B)
-        kp = self._labels_dev(probe_label, B)
-        s = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
-            self.n_ones.zero_()
-            # ffc.py:162-177 / 214-235: LRU get/try_get + row/col bookkeeping, on the device
-            self._lru.assign(kg, journal=not commit, qpos=self.qpos, rows=self.rows, cols=self.cols, ones_list=self.ones_list,
-                            n_ones=self.n_ones, cmask=self.cmask)
-            # ffc.py:179-182 / 237-241: enqueue (fp32 queue + bf16 mirror), old rows saved on a rollback pass
-            check(lib.ffc_queue_scatter(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
-                                        g32.data_ptr(), B, Q, D, None if commit else self.undo_rows.data_ptr(), s))
-            # ffc.py:189-194 / 242-246: probe labels after this pass's inserts
-            self._lru.view_batch(kp, self.label)
-            st = self.stats
-            hp = HeadPass(p32.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.label.data_ptr(),
-                          self.ones_list.data_ptr(), self.n_ones.data_ptr(), self.cmask.data_ptr(), B)
-            hs = HeadStats(*(self._stat_ptr(name, B) for name in ('lsum', 'osum', 'tgt', 'topv', 'topi')))
-            self.loss_buf.zero_()
-            dp = torch.empty(B, D, dtype=torch.float32, device=dev)
-            # ffc.py:195-202 / 248-254 + backward
-            check(lib.ffc_head_sweep(self._h, C.byref(hp), C.byref(hs), s))
-            check(lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), 1, self.loss_buf.data_ptr(), dp.data_ptr(), s))
-            loss = self.loss_buf[0].clone()
-            if not commit:   # ffc.py:255-259
-                check(lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
-                                            self.undo_rows.data_ptr(), B, Q, D, s))
-                self._lru.undo(B, self.qpos)
-            self.cmask.zero_()
-            self._last = dict(rows=self.rows[:B], cols=self.cols[:B], label=self.label[:B], ones=self.ones_list, n_ones=self.n_ones)
-        return loss, dp
+        return B
+
+    @staticmethod
+    def _on_device(lab):
+        return torch.is_tensor(lab) and lab.is_cuda
+
+    def _pass(self, p, g, probe_label, gallery_label, commit):
+        self._ensure()
+        B = self._check_batch(p, g)
+        with torch.cuda.device(self._dev):
+            main = torch.cuda.current_stream(self._dev)
+            done = self._bookkeep(0 if not commit else 1, gallery_label, probe_label, B, commit, main,
+                                  self._on_device(probe_label) or self._on_device(gallery_label))
+            main.wait_event(done)
+            return self._finish(0 if not commit else 1, p, g, B, commit, main)
+
+    def forward_pair(self, p_rb, g_rb, p_cm, g_cm, x_label, y_label):
+        """ffc.py:264-267 with embeddings in and no autograd glue: the rollback pass (probe p_rb with labels x_label, gallery g_rb
+        with labels y_label) then the commit pass (probe p_cm / y_label, gallery g_cm / x_label).  Both passes' LRU bookkeeping is
+        enqueued first on the bookkeeping stream -- a rollback pass leaves the LRU as it found it, so the commit pass's
+        bookkeeping does not depend on the rollback sweep and runs underneath it (on the SMs the sweep leaves free); with host
+        labels (the reference's contract, main.py:59-60) it even runs under the previous step's sweep.
+        Returns (loss1 + loss2, dLoss/dp_rb, dLoss/dp_cm)."""
+        self._ensure()
+        B = self._check_batch(p_rb, g_rb)
+        assert self._check_batch(p_cm, g_cm) == B
+        with torch.cuda.device(self._dev):
+            main = torch.cuda.current_stream(self._dev)
+            on_main = self._on_device(x_label) or self._on_device(y_label)
+            done_rb = self._bookkeep(0, y_label, x_label, B, False, main, on_main)
+            done_cm = self._bookkeep(1, x_label, y_label, B, True, main, False)
+            main.wait_event(done_rb)
+            l2, d_rb = self._finish(0, p_rb, g_rb, B, False, main)
+            main.wait_event(done_cm)
+            l1, d_cm = self._finish(1, p_cm, g_cm, B, True, main)
+        return l1 + l2, d_rb, d_cm
+
+    def forward(self, x, y, x_label, y_label):
+        """``FFC.forward`` (ffc.py:264-267) with embeddings in: ``x`` / ``y`` are the two views' embeddings [B, D]; gradients flow
+        to both (each is the probe of one pass and the no-grad gallery of the other)."""
+        return _HeadPairFn.apply(x, y, self, y.detach(), x.detach(), x_label, y_label)
 
     def _stat_ptr(self, name, B):
         # the stats arrays are laid out [slots][n_rows][...] for the n_rows of THIS pass: use compact per-pass views
@@ -290,6 +379,14 @@ class FFC(FFCHead):
         return self.head(p, g, probe_label, gallery_label, commit=False)
 
     def forward(self, x, y, x_label, y_label):                                     # ffc.py:264-267
-        loss2 = self.forward_impl_rollback(x, y, x_label, y_label)
-        loss1 = self.forward_impl(y, x, y_label, x_label)
-        return loss1 + loss2
+        """loss2 = forward_impl_rollback(x, y, ...), loss1 = forward_impl(y, x, ...), returned as loss1 + loss2.  The four backbone
+        calls are issued in the reference's order (probe(x), EMA, gallery(y), probe(y), gallery(x)); the two head passes then
+        run as one pair so that their bookkeeping overlaps the sweeps."""
+        p_rb = self.probe_net(x)
+        with torch.no_grad():
+            self._momentum_update_gallery()
+            g_rb = self.gallery_net(y)
+        p_cm = self.probe_net(y)
+        with torch.no_grad():
+            g_cm = self.gallery_net(x)
+        return _HeadPairFn.apply(p_rb, p_cm, self, g_rb, g_cm, x_label, y_label)
