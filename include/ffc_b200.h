@@ -176,13 +176,20 @@ typedef struct ffc_head_stats {
 
 int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream);
 
-/* Finalize: loss_out[0] += this pass's loss (both add_margin terms) -- identical on every rank when
+/* Finalize: loss_out[0] = this pass's loss (both add_margin terms) -- identical on every rank when
  * stats were reduced; dp_out [n_rows, D] fp32 = this rank's contribution to dLoss/dp (the whole
  * gradient on one GPU).  n_ranks_topk: number of gathered top-k candidate sets in stats->topv/topi
  * ([n_ranks][3][n][k]); 1 on one GPU.  n_pos/n_out (global counts of label!=-1 / ==-1 rows) are
  * computed on the device from `label`. */
 int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats,
                       int n_ranks_topk, float* loss_out, float* dp_out, void* stream);
+
+/* One-GPU fast path: ffc_head_sweep + ffc_head_finalize(n_ranks_topk = 1) as one call.  On the bf16 AM / Arc path the chunk
+ * reduction, the scalar part and dLoss/dp run as ONE kernel after the sweep (the statistics never round-trip through HBM, so
+ * `scratch` is left partly unwritten: only tgt is filled); other configurations run the two calls back to back.
+ * Replaces ffc.py:195-202 / 248-254 + loss.backward() of one head pass. */
+int ffc_head_pass_single(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* scratch,
+                         float* loss_out, float* dp_out, void* stream);
 
 /* sizes in bytes of the five stats arrays for n rows (one rank's worth) */
 int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]);

@@ -15,6 +15,10 @@
 
 #include "head_internal.cuh"
 
+namespace ffc {
+struct ReduceJobs;
+}
+
 struct ffc_head {
   ffc_head_config cfg;
   int64_t part_rows_cap;
@@ -27,7 +31,10 @@ struct ffc_head {
   int32_t* tpos;               // [max_rows]  target position in ones_list or -1
   uint8_t* is_out;             // [max_rows]
   float* thr;                  // [2][max_rows]
-  int32_t* counts;             // [2] n_pos, n_out
+  int32_t* counts;             // [2][2] n_pos, n_out, double-buffered by pass parity
+  int pass_parity;
+  ffc::ReduceJobs* jobs;        // partial-result descriptors of the last merged sweep launch (one-GPU fast path)
+  int jobs_pending;            // 1: the last sweep left its partials unreduced for head_finalize_fused_kernel
   float* row_loss;             // [max_rows]
   float* coef;                 // [4][max_rows] finalize coefficients
   int32_t* nslot;              // [max_rows] hard-negative gather count
@@ -145,6 +152,104 @@ __global__ void __launch_bounds__(128) head_target_kernel(const float* __restric
     if (thr) {
       thr[i] = tc >= 0 ? c0 - margin : INFINITY;
       thr[n_rows + i] = tc >= 0 ? c1 - margin : INFINITY;
+    }
+  }
+}
+
+// Everything a pass needs before its sweep, in ONE launch (block b: probe row b and/or side row b):
+//   row part   (b < n_rows): target column / position in `ones` / outlier flag / n_pos, n_out counts (head_prep_rows_kernel),
+//                            bf16 copy of the probe row (head_p_to_bf16_kernel), target cosines (head_target_kernel)
+//   side part  (b < ceil128(n_ones)): gathered `ones` rows of queue[0] and queue[1] (head_gather_side_kernel)
+// counts[2][2] is double-buffered by pass parity: block 0 clears the other parity's pair for the next pass (no memset launch).
+template <bool BF16>
+__global__ void __launch_bounds__(128) head_prep_fused_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ P16, const int32_t* __restrict__ label,
+                                                              int n_rows, int64_t col_offset, int64_t q_local, int D, const float* __restrict__ qf,
+                                                              const __nv_bfloat16* __restrict__ qh, const uint32_t* __restrict__ cmask,
+                                                              const int32_t* __restrict__ ones_list, const int32_t* __restrict__ n_ones_p, int max_rows,
+                                                              float* __restrict__ side_f32, __nv_bfloat16* __restrict__ side_bf16,
+                                                              int32_t* __restrict__ tcol, int32_t* __restrict__ tpos, uint8_t* __restrict__ is_out,
+                                                              int32_t* counts_cur, int32_t* counts_next, float margin, float* __restrict__ tgt,
+                                                              float* __restrict__ thr) {
+  const int b = blockIdx.x;
+  const int no = *n_ones_p;
+  __shared__ int found;
+  __shared__ double s0[128], s1[128];
+  if (b == 0 && threadIdx.x < 2) counts_next[threadIdx.x] = 0;
+  if (b < n_rows) {
+    const int i = b;
+    const int32_t lab = label[i];
+    int32_t tc = -1;
+    if (lab >= 0) {
+      const int64_t loc = (int64_t)lab - col_offset;
+      if (loc >= 0 && loc < q_local) tc = (int32_t)loc;
+    }
+    if (threadIdx.x == 0) found = -1;
+    __syncthreads();
+    const bool in_c = (tc >= 0) && cmask && ((cmask[tc >> 5] >> (tc & 31)) & 1u);
+    if (in_c) {
+      for (int j = threadIdx.x; j < no; j += blockDim.x)
+        if (ones_list[j] == tc) found = j;
+    }
+    __syncthreads();
+    const int fpos = found;
+    if (threadIdx.x == 0) {
+      tcol[i] = tc;
+      tpos[i] = fpos;
+      is_out[i] = lab < 0;
+      atomicAdd(&counts_cur[lab < 0 ? 1 : 0], 1);
+    }
+    // bf16 probe row + target cosines: tgt[0] = p . queue[0][t], tgt[1] = p . (t in C ? queue[1][t] : queue[0][t])
+    double a0 = 0.0, a1 = 0.0;
+    const int64_t r0 = (int64_t)(tc >= 0 ? tc : 0) * D;
+    const int64_t r1 = (fpos >= 0) ? ((int64_t)q_local + tc) * D : r0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float p = P[(int64_t)i * D + d];
+      if (BF16) {
+        const __nv_bfloat16 pb = __float2bfloat16(p);
+        P16[(int64_t)i * D + d] = pb;
+        p = __bfloat162float(pb);
+      }
+      if (tc >= 0) {
+        const float w0 = BF16 ? __bfloat162float(qh[r0 + d]) : qf[r0 + d];
+        const float w1 = BF16 ? __bfloat162float(qh[r1 + d]) : qf[r1 + d];
+        a0 += (double)p * w0;
+        a1 += (double)p * w1;
+      }
+    }
+    s0[threadIdx.x] = a0;
+    s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        s0[threadIdx.x] += s0[threadIdx.x + o];
+        s1[threadIdx.x] += s1[threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const float c0 = (float)s0[0], c1 = (float)s1[0];
+      tgt[0 * n_rows + i] = tc >= 0 ? c0 : 0.f;
+      tgt[1 * n_rows + i] = tc >= 0 ? c1 : 0.f;
+      tgt[2 * n_rows + i] = tc >= 0 ? 1.f : 0.f;
+      tgt[3 * n_rows + i] = 0.f;
+      if (thr) {
+        thr[i] = tc >= 0 ? c0 - margin : INFINITY;
+        thr[n_rows + i] = tc >= 0 ? c1 - margin : INFINITY;
+      }
+    }
+  }
+  // side matrices: W_side0[j] = queue[0][ones[j]], W_side1[j] = queue[1][ones[j]], zero padded to the 128-row tile
+  if (b < ((no + 127) & ~127) && b < max_rows) {
+    const int j = b;
+    const bool live = j < no;
+    const int64_t slot = live ? ones_list[j] : 0;
+    for (int r = 0; r < 2; ++r) {
+      const int64_t src = ((int64_t)r * q_local + slot) * D;
+      const int64_t dst = ((int64_t)r * max_rows + j) * D;
+      for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        if (side_f32) side_f32[dst + d] = live ? qf[src + d] : 0.f;
+        if (side_bf16) side_bf16[dst + d] = live ? qh[src + d] : __float2bfloat16(0.f);
+      }
     }
   }
 }
@@ -441,17 +546,16 @@ __device__ __forceinline__ float w_elem(const FinalizeArgs& a, int r, int64_t lo
   return a.use_bf16_rows ? __bfloat162float(a.qh[off]) : a.qf[off];
 }
 
-// Pass 1, one THREAD per row: the scalar part of finalize (margin function, log/exp in fp64, top-k merge).  Doing this
-// per thread instead of on thread 0 of a per-row block keeps the fp64 transcendental latency off the critical path.
-__global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a, float* __restrict__ coef, int32_t* __restrict__ nslot,
-                                                            int32_t* __restrict__ wslot, uint8_t* __restrict__ wrow) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// The scalar part of finalize for one row: margin function, log/exp in fp64, top-k merge.  `lsum_at(slot)` returns the row's
+// softmax denominator of stats slot 0..3, `top_at(r, set, q, v, idx)` the q-th top-k candidate of rank r / column set `set`.
+template <class LsumF, class TopF>
+__device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int n_ranks, LsumF lsum_at, TopF top_at, float& loss_out, float (&cO)[2],
+                                              float (&cT)[2], int& nw_out, int32_t* wslot_out, uint8_t* wrow_out) {
   const int n = a.n, k = a.k;
-  if (i >= n) return;
   const int n_pos = a.counts[0], n_out = a.counts[1];
   const bool outl = a.is_out[i];
   float loss = 0.f;
-  float cO[2] = {0.f, 0.f}, cT[2] = {0.f, 0.f};
+  cO[0] = cO[1] = cT[0] = cT[1] = 0.f;
   int nw = 0;
   if (!outl) {
     const double s = a.scale, M = a.fixed_max, m = a.margin;
@@ -476,7 +580,7 @@ __global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a
       const double zt = s * ft;
       const double et = exp(zt - M);
       const int cs = a.loss_type == FFC_LOSS_SV ? l : 0;   // common-statistics slot
-      const double L = (double)a.lsum[cs * n + i] + (double)a.lsum[(2 + l) * n + i] + et;
+      const double L = (double)lsum_at(cs) + (double)lsum_at(2 + l) + et;
       loss += (float)((log(L) + M - zt) / (double)n_pos);
       cO[l] = (float)(s / L / (double)n_pos);
       cT[l] = (float)(s * (et / L - 1.0) * dft / (double)n_pos);
@@ -492,14 +596,15 @@ __global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a
         tv[q] = -INFINITY;
         ti[q] = -1;
       }
-      for (int r = 0; r < a.n_ranks; ++r)
+      for (int r = 0; r < n_ranks; ++r)
         for (int src = 0; src < 2; ++src) {
           const int set = src == 0 ? 0 : 1 + l;
-          const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
           for (int q = 0; q < k; ++q) {
-            const float v = a.topv[base + q];
+            float v;
+            int32_t idx;
+            top_at(r, set, q, v, idx);
             // a side entry is tagged in bit 30: under loss 2 it reads queue[1]
-            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, (int32_t)(a.topi[base + q] | (src ? 0x40000000 : 0)));
+            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, (int32_t)(idx | (src ? 0x40000000 : 0)));
           }
         }
       for (int q = 0; q < k; ++q) {
@@ -507,19 +612,139 @@ __global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a
         const float v = tv[q];
         loss += (v > 0.f ? v : 0.f) * wneg;
         if (v >= 0.f) {
-          wslot[(int64_t)i * 2 * KMAX + nw] = ti[q] & 0x3fffffff;
-          wrow[(int64_t)i * 2 * KMAX + nw] = (ti[q] & 0x40000000) ? (uint8_t)l : (uint8_t)0;
+          wslot_out[nw] = ti[q] & 0x3fffffff;
+          wrow_out[nw] = (ti[q] & 0x40000000) ? (uint8_t)l : (uint8_t)0;
           ++nw;
         }
       }
     }
   }
+  loss_out = loss;
+  nw_out = nw;
+}
+
+// Pass 1, one THREAD per row: the scalar part of finalize.  Doing this per thread instead of on thread 0 of a per-row block
+// keeps the fp64 transcendental latency off the critical path.
+__global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a, float* __restrict__ coef, int32_t* __restrict__ nslot,
+                                                            int32_t* __restrict__ wslot, uint8_t* __restrict__ wrow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = a.n, k = a.k;
+  if (i >= n) return;
+  float loss, cO[2], cT[2];
+  int nw;
+  row_coef_math(
+      a, i, a.n_ranks, [&](int slot) { return a.lsum[slot * n + i]; },
+      [&](int r, int set, int q, float& v, int32_t& idx) {
+        const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
+        v = a.topv[base + q];
+        idx = a.topi[base + q];
+      },
+      loss, cO, cT, nw, wslot + (int64_t)i * 2 * KMAX, wrow + (int64_t)i * 2 * KMAX);
   a.row_loss[i] = loss;
   coef[0 * n + i] = cO[0];
   coef[1 * n + i] = cO[1];
   coef[2 * n + i] = cT[0];
   coef[3 * n + i] = cT[1];
   nslot[i] = nw;
+}
+
+// One-GPU fast path of the bf16 AM / Arc head: chunk reduction of the three sweeps' partials, the scalar part and dLoss/dp in
+// ONE launch (block = row).  No osum / lsum / top-k round trip through HBM; replaces reduce + row_coef + finalize.
+__global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a) {
+  const int i = blockIdx.x, n = a.n, D = a.D, k = a.k;
+  __shared__ float s_l[3];
+  __shared__ float s_tv[3][KMAX];
+  __shared__ int32_t s_ti[3][KMAX];
+  __shared__ float s_coef[4];
+  __shared__ int s_nw;
+  __shared__ int32_t s_wslot[2 * KMAX];
+  __shared__ uint8_t s_wrow[2 * KMAX];
+  const bool outl = a.is_out[i];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < 3 && lane == 0) {
+    const ReduceJob& r = jobs.j[w];
+    float acc = 0.f;
+    for (int c = 0; c < r.n_chunks; ++c) acc += r.l_part[(int64_t)c * n + i];
+    s_l[w] = acc;
+    float tv[KMAX];
+    int32_t ti[KMAX];
+    for (int q = 0; q < KMAX; ++q) {
+      tv[q] = -INFINITY;
+      ti[q] = -1;
+    }
+    if (outl) {
+      for (int c = 0; c < r.n_chunks; ++c)
+        for (int q = 0; q < k; ++q) {
+          const float v = r.topv_part[((int64_t)c * n + i) * k + q];
+          if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, r.topi_part[((int64_t)c * n + i) * k + q]);
+        }
+    }
+    for (int q = 0; q < KMAX; ++q) {
+      int32_t id = ti[q];
+      if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
+      s_tv[w][q] = tv[q];
+      s_ti[w][q] = id;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float loss, cO[2], cT[2];
+    int nw;
+    row_coef_math(
+        a, i, 1, [&](int slot) { return slot == 0 ? s_l[0] : (slot >= 2 ? s_l[slot - 1] : 0.f); },
+        [&](int, int set, int q, float& v, int32_t& idx) {
+          v = s_tv[set][q];
+          idx = s_ti[set][q];
+        },
+        loss, cO, cT, nw, s_wslot, s_wrow);
+    a.row_loss[i] = loss;
+    s_coef[0] = cO[0];
+    s_coef[1] = cO[1];
+    s_coef[2] = cT[0];
+    s_coef[3] = cT[1];
+    s_nw = nw;
+  }
+  __syncthreads();
+  const float cO0 = s_coef[0], cO1 = s_coef[1], cT0 = s_coef[2], cT1 = s_coef[3];
+  const int32_t tc = a.tcol[i];
+  const int trow2 = (a.tpos[i] >= 0) ? 1 : 0;
+  const int nw = s_nw;
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!outl) {
+      float o[3][4];
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb) {
+        const ReduceJob& r = jobs.j[jb];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < r.n_chunks; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(r.o_part + ((int64_t)c * n + i) * D + d);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+        o[jb][0] = acc.x;
+        o[jb][1] = acc.y;
+        o[jb][2] = acc.z;
+        o[jb][3] = acc.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[e] = cO0 * (o[0][e] + o[1][e]) + cO1 * (o[0][e] + o[2][e]);
+        if (tc >= 0) g[e] += cT0 * w_elem(a, 0, tc, d + e) + cT1 * w_elem(a, trow2, tc, d + e);
+      }
+    } else {
+      for (int x = 0; x < nw; ++x) {
+        const int64_t loc = (int64_t)s_wslot[x] - a.col_offset;
+        if (loc >= 0 && loc < a.q_local) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) g[e] += cO0 * w_elem(a, s_wrow[x], loc, d + e);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(a.dp + (int64_t)i * D + d) = make_float4(g[0], g[1], g[2], g[3]);
+  }
 }
 
 // Pass 2, one block per row: dLoss/dp from the accumulated sums (bandwidth bound).
@@ -558,7 +783,7 @@ __global__ void __launch_bounds__(1024) head_loss_sum_kernel(const float* __rest
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) loss_out[0] += (float)sh[0];
+  if (threadIdx.x == 0) loss_out[0] = (float)sh[0];
 }
 
 __global__ void head_p_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -608,7 +833,8 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_CUDA(cudaMalloc(&h->tpos, R * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->is_out, R));
   FFC_CUDA(cudaMalloc(&h->thr, 2 * R * sizeof(float)));
-  FFC_CUDA(cudaMalloc(&h->counts, 2 * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->counts, 4 * sizeof(int32_t)));
+  FFC_CUDA(cudaMemset(h->counts, 0, 4 * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->row_loss, R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->coef, 4 * R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->nslot, R * sizeof(int32_t)));
@@ -620,6 +846,7 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_CUDA(cudaMalloc(&h->topi_part, h->part_rows_cap * KMAX * sizeof(int32_t)));
   if (cfg->precision == FFC_PREC_BF16) h->sm100 = sm100_cache_create();
   h->ev = new std::vector<cudaEvent_t>();
+  h->jobs = new ReduceJobs();
   *out = h;
   return FFC_OK;
 }
@@ -648,6 +875,7 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
     for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
     delete h->ev;
   }
+  delete h->jobs;
   delete h;
   return FFC_OK;
 }
@@ -689,7 +917,7 @@ static int run_one_sweep(ffc_head* h, SweepArgs a, int cache_slot, int stat_slot
 
 // bf16, AM / Arc: the main sweep over queue[0] and the two side sweeps over the gathered `ones` rows of queue[0] / queue[1] as ONE
 // launch of the tcgen05 kernel (their items are concatenated), followed by one reduce launch.
-static int run_merged_sweeps(ffc_head* h, SweepArgs a, const ffc_head_pass* in, const ffc_head_stats* out, cudaStream_t s) {
+static int run_merged_sweeps(ffc_head* h, SweepArgs a, const ffc_head_pass* in, const ffc_head_stats* out, bool defer_reduce, cudaStream_t s) {
   const ffc_head_config& c = h->cfg;
   const int n = a.n_rows, D = a.D, k = a.k;
   SweepArgs sw[3];
@@ -752,13 +980,18 @@ static int run_merged_sweeps(ffc_head* h, SweepArgs a, const ffc_head_pass* in, 
     FFC_CUDA(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
     h->ev_used += 2;
   }
-  head_reduce_multi_kernel<<<dim3(n, 3), 128, 0, s>>>(jobs, n, D, k, a.is_out);
-  FFC_LAUNCH_CHECK();
+  *h->jobs = jobs;
+  h->jobs_pending = defer_reduce ? 1 : 0;
+  if (!defer_reduce) {
+    head_reduce_multi_kernel<<<dim3(n, 3), 128, 0, s>>>(jobs, n, D, k, a.is_out);
+    FFC_LAUNCH_CHECK();
+  }
   return FFC_OK;
 }
 
-extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
+static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, bool defer_reduce, void* stream) {
   FFC_REQUIRE(h && in && out, "ffc_head_sweep: NULL argument");
+  h->jobs_pending = 0;
   const ffc_head_config& c = h->cfg;
   const int n = in->n_rows, D = c.feat_dim;
   FFC_REQUIRE(n >= 1 && n <= c.max_rows, "ffc_head_sweep: n_rows=%d outside [1,%d]", n, c.max_rows);
@@ -770,23 +1003,23 @@ extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   const float* qf = in->queue_f32;
   const __nv_bfloat16* qh = (const __nv_bfloat16*)in->queue_bf16;
 
-  FFC_CUDA(cudaMemsetAsync(h->counts, 0, 2 * sizeof(int32_t), s));
-  head_prep_rows_kernel<<<n, 128, 0, s>>>(in->label, n, c.col_offset, c.q_local, in->cmask, in->ones_list, in->n_ones, h->tcol, h->tpos, h->is_out,
-                                          h->counts);
-  FFC_LAUNCH_CHECK();
-  head_gather_side_kernel<<<c.max_rows, 128, 0, s>>>(qf, qh, c.q_local, D, in->ones_list, in->n_ones, c.max_rows, bf16 ? nullptr : h->side_f32,
-                                                     bf16 ? h->side_bf16 : nullptr);
-  FFC_LAUNCH_CHECK();
-  if (bf16) {
-    head_p_to_bf16_kernel<<<(int)std::min<int64_t>(ceil_div64((int64_t)n * D, 256), 1184), 256, 0, s>>>(in->p_f32, h->p16, (int64_t)n * D);
+  const bool sv = c.loss_type == FFC_LOSS_SV;
+  {
+    // counts double-buffered by pass parity (see head_prep_fused_kernel)
+    h->pass_parity ^= 1;
+    int32_t* cur = h->counts + 2 * h->pass_parity;
+    int32_t* nxt = h->counts + 2 * (h->pass_parity ^ 1);
+    const int grid = std::min<int>(c.max_rows, (n + 127) & ~127);
+    if (bf16)
+      head_prep_fused_kernel<true><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
+                                                        in->n_ones, c.max_rows, nullptr, h->side_bf16, h->tcol, h->tpos, h->is_out, cur, nxt, c.margin,
+                                                        out->tgt, sv ? h->thr : nullptr);
+    else
+      head_prep_fused_kernel<false><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
+                                                         in->n_ones, c.max_rows, h->side_f32, nullptr, h->tcol, h->tpos, h->is_out, cur, nxt, c.margin,
+                                                         out->tgt, sv ? h->thr : nullptr);
     FFC_LAUNCH_CHECK();
   }
-  const bool sv = c.loss_type == FFC_LOSS_SV;
-  if (bf16)
-    head_target_kernel<true><<<n, 128, 0, s>>>(in->p_f32, h->p16, qf, qh, c.q_local, D, n, h->tcol, h->tpos, c.margin, out->tgt, sv ? h->thr : nullptr);
-  else
-    head_target_kernel<false><<<n, 128, 0, s>>>(in->p_f32, h->p16, qf, qh, c.q_local, D, n, h->tcol, h->tpos, c.margin, out->tgt, sv ? h->thr : nullptr);
-  FFC_LAUNCH_CHECK();
 
   SweepArgs a;
   memset(&a, 0, sizeof(a));
@@ -800,7 +1033,7 @@ extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   a.sv = sv;
   a.k = c.topk;
   int rc;
-  if (bf16 && !sv) return run_merged_sweeps(h, a, in, out, s);
+  if (bf16 && !sv) return run_merged_sweeps(h, a, in, out, defer_reduce, s);
   // main sweep(s) over queue[0]: everything except the target column and the `ones` columns
   a.W_f32 = qf;
   a.W_bf16 = qh;
@@ -828,8 +1061,28 @@ extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   return FFC_OK;
 }
 
+extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
+  return head_sweep_impl(h, in, out, false, stream);
+}
+
+static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out, float* dp_out,
+                              void* stream);
+
+extern "C" int ffc_head_pass_single(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* scratch, float* loss_out, float* dp_out, void* stream) {
+  FFC_REQUIRE(h && in && scratch && loss_out && dp_out, "ffc_head_pass_single: NULL argument");
+  int rc = head_sweep_impl(h, in, scratch, true, stream);
+  if (rc) return rc;
+  return head_finalize_impl(h, in, scratch, 1, loss_out, dp_out, stream);
+}
+
 extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out,
                                  float* dp_out, void* stream) {
+  FFC_REQUIRE(h && !h->jobs_pending, "ffc_head_finalize: the last sweep was issued by ffc_head_pass_single");
+  return head_finalize_impl(h, in, stats, n_ranks_topk, loss_out, dp_out, stream);
+}
+
+static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out, float* dp_out,
+                              void* stream) {
   FFC_REQUIRE(h && in && stats && loss_out && dp_out, "ffc_head_finalize: NULL argument");
   FFC_REQUIRE(n_ranks_topk >= 1, "ffc_head_finalize: n_ranks_topk must be >= 1");
   const ffc_head_config& c = h->cfg;
@@ -843,7 +1096,7 @@ extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const f
   a.tcol = h->tcol;
   a.tpos = h->tpos;
   a.is_out = h->is_out;
-  a.counts = h->counts;
+  a.counts = h->counts + 2 * h->pass_parity;
   a.lsum = stats->lsum;
   a.osum = stats->osum;
   a.tgt = stats->tgt;
@@ -861,10 +1114,17 @@ extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const f
   a.fixed_max = fixed_max_of(c);
   a.row_loss = h->row_loss;
   a.dp = dp_out;
-  head_row_coef_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
-  FFC_LAUNCH_CHECK();
-  head_finalize_kernel<<<a.n, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
-  FFC_LAUNCH_CHECK();
+  if (h->jobs_pending) {       // one-GPU fast path: the sweep left its partials for the fused reduce + finalize
+    FFC_REQUIRE(n_ranks_topk == 1, "fused finalize is single-rank");
+    h->jobs_pending = 0;
+    head_finalize_fused_kernel<<<a.n, 128, 0, s>>>(*h->jobs, a);
+    FFC_LAUNCH_CHECK();
+  } else {
+    head_row_coef_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
+    FFC_LAUNCH_CHECK();
+    head_finalize_kernel<<<a.n, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
+    FFC_LAUNCH_CHECK();
+  }
   head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
   FFC_LAUNCH_CHECK();
   return FFC_OK;

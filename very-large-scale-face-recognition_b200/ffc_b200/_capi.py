@@ -54,6 +54,7 @@ PROTOTYPES = {
     'ffc_head_destroy': (c_int, [c_void_p]),
     'ffc_head_sweep': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_void_p]),
     'ffc_head_finalize': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_int, c_void_p, c_void_p, c_void_p]),
+    'ffc_head_pass_single': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_void_p, c_void_p, c_void_p]),
     'ffc_head_set_timing': (c_int, [c_void_p, c_int]),
     'ffc_head_get_timing': (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64)]),
     'ffc_head_stats_bytes': (c_int, [C.POINTER(HeadConfig), c_int, C.POINTER(c_int64)]),

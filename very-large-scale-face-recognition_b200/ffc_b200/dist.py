@@ -130,10 +130,10 @@ class CudaShardBackend:
 
     def finalize(self, p_all, label, st, n_ranks):
         hp, hs = self._structs(p_all, label, st, 0)
-        self.loss_buf.zero_()
         dp = torch.empty(p_all.shape[0], self.D, dtype=torch.float32, device=self.dev)
-        check(self.lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), n_ranks, self.loss_buf.data_ptr(), dp.data_ptr(), self._s()))
-        return self.loss_buf[0].clone(), dp
+        loss = torch.empty((), dtype=torch.float32, device=self.dev)
+        check(self.lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), n_ranks, loss.data_ptr(), dp.data_ptr(), self._s()))
+        return loss, dp
 
     def end_pass(self):
         self.cmask.zero_()

@@ -255,12 +255,10 @@ class FFCHead(Module):
         hp = HeadPass(p32.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.label.data_ptr(),
                       self.ones_list.data_ptr(), self.n_ones.data_ptr(), self.cmask.data_ptr(), B)
         hs = HeadStats(*(self._stat_ptr(name, B) for name in ('lsum', 'osum', 'tgt', 'topv', 'topi')))
-        self.loss_buf.zero_()
         dp = torch.empty(B, D, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
         # ffc.py:195-202 / 248-254 + backward
-        check(lib.ffc_head_sweep(self._h, C.byref(hp), C.byref(hs), s))
-        check(lib.ffc_head_finalize(self._h, C.byref(hp), C.byref(hs), 1, self.loss_buf.data_ptr(), dp.data_ptr(), s))
-        loss = self.loss_buf[0].clone()
+        check(lib.ffc_head_pass_single(self._h, C.byref(hp), C.byref(hs), loss.data_ptr(), dp.data_ptr(), s))
         if not commit:   # ffc.py:255: the queue rows come back; the LRU was undone by the bookkeeping stream
             check(lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
                                         self.undo_rows.data_ptr(), B, Q, D, s))
