@@ -112,6 +112,15 @@ int ffc_lru_import(ffc_lru_t* h, const int64_t* keys_host, const int32_t* slots_
 int ffc_queue_scatter(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
                       const int32_t* cols_dev, const float* g_dev, int B, int64_t Q, int D,
                       float* undo_f32_dev, void* stream);
+/* as ffc_queue_scatter with g[src_row[i], :] as the source row of position i (the sharded head scatters straight out of the
+ * all-gathered embeddings) */
+int ffc_queue_scatter_indexed(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
+                              const int32_t* cols_dev, const float* g_dev, const int32_t* src_row_dev, int B,
+                              int64_t Q, int D, float* undo_f32_dev, void* stream);
+/* Sharded head: stable partition of n gathered gallery keys into (keys owned by `rank` under key mod n_ranks, the rest);
+ * keys_out / order_out [n] (order_out[j] = source position), n_mine_out device scalar. */
+int ffc_route_keys(const int64_t* keys_dev, int n, int n_ranks, int rank, int64_t* keys_out_dev,
+                   int32_t* order_out_dev, int32_t* n_mine_out_dev, void* stream);
 int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
                       const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
                       void* stream);
@@ -190,6 +199,16 @@ int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_sta
  * Replaces ffc.py:195-202 / 248-254 + loss.backward() of one head pass. */
 int ffc_head_pass_single(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* scratch,
                          float* loss_out, float* dp_out, void* stream);
+
+/* Sharded head (ffc_b200/dist.py; nothing like it in the reference): instead of ffc_head_sweep + all-reduce + all-gather +
+ * ffc_head_finalize, a rank writes ONE record per pass (softmax denominators, target cosines, top-k candidates;
+ * ffc_head_record_words 4-byte words), the records of all ranks are exchanged by one all-gather, and
+ * ffc_head_finalize_gathered sums the scalars in rank order and produces this rank's partial dLoss/dp straight from its
+ * sweep partials.  bf16 AM / Arc only. */
+int ffc_head_record_words(const ffc_head_config* cfg, int n_rows, int64_t* words_out);
+int ffc_head_sweep_record(ffc_head_t* h, const ffc_head_pass* in, void* record_out, void* stream);
+int ffc_head_finalize_gathered(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks,
+                               int64_t record_stride_words, float* loss_out, float* dp_out, void* stream);
 
 /* sizes in bytes of the five stats arrays for n rows (one rank's worth) */
 int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]);

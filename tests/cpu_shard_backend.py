@@ -60,7 +60,8 @@ class CpuShardBackend:
             self.cols.append(s)
         self.journal = journal
 
-    def scatter(self, g_compact, save_undo):
+    def scatter(self, g_all, order, save_undo):
+        g_compact = g_all[order]
         last = {}
         for i, rc in enumerate(zip(self.rows, self.cols)):
             last[rc] = i

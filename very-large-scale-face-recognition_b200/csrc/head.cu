@@ -548,8 +548,8 @@ __device__ __forceinline__ float w_elem(const FinalizeArgs& a, int r, int64_t lo
 
 // The scalar part of finalize for one row: margin function, log/exp in fp64, top-k merge.  `lsum_at(slot)` returns the row's
 // softmax denominator of stats slot 0..3, `top_at(r, set, q, v, idx)` the q-th top-k candidate of rank r / column set `set`.
-template <class LsumF, class TopF>
-__device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int n_ranks, LsumF lsum_at, TopF top_at, float& loss_out, float (&cO)[2],
+template <class LsumF, class TgtF, class TopF>
+__device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int n_ranks, LsumF lsum_at, TgtF tgt_at, TopF top_at, float& loss_out, float (&cO)[2],
                                               float (&cT)[2], int& nw_out, int32_t* wslot_out, uint8_t* wrow_out) {
   const int n = a.n, k = a.k;
   const int n_pos = a.counts[0], n_out = a.counts[1];
@@ -560,7 +560,7 @@ __device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int 
   if (!outl) {
     const double s = a.scale, M = a.fixed_max, m = a.margin;
     for (int l = 0; l < 2; ++l) {
-      double ct = a.tgt[l * n + i];
+      double ct = tgt_at(l);
       // bf16 operands are rounded, so a cosine of two (nearly) identical unit vectors can land a few ulp outside
       // [-1, 1] and turn ffc.py:101's sqrt into NaN where the fp32 reference is finite: keep it strictly inside.
       // The fp32 check mode does not clamp and propagates NaN exactly like the reference.
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a
   float loss, cO[2], cT[2];
   int nw;
   row_coef_math(
-      a, i, a.n_ranks, [&](int slot) { return a.lsum[slot * n + i]; },
+      a, i, a.n_ranks, [&](int slot) { return a.lsum[slot * n + i]; }, [&](int l) { return a.tgt[l * n + i]; },
       [&](int r, int set, int q, float& v, int32_t& idx) {
         const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
         v = a.topv[base + q];
@@ -648,9 +648,55 @@ __global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a
   nslot[i] = nw;
 }
 
-// One-GPU fast path of the bf16 AM / Arc head: chunk reduction of the three sweeps' partials, the scalar part and dLoss/dp in
-// ONE launch (block = row).  No osum / lsum / top-k round trip through HBM; replaces reduce + row_coef + finalize.
-__global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a) {
+// Per-rank record exchanged by the sharded head (4-byte words, n = rows, k = top-k):
+//   [0, 8n)          float  red[8][n]     lsum slots 0..3 (common loss 1, unused, side 0, side 1), tgt slots 0..3
+//   [8n, 8n+3nk)     float  topv[3][n][k]
+//   [8n+3nk, +3nk)   int32  topi[3][n][k] GLOBAL slots
+__host__ __device__ __forceinline__ int64_t record_words(int64_t n, int64_t k) { return 8 * n + 6 * n * k; }
+
+// Chunk reduction of the three sweeps' SCALAR partials (softmax denominators, top-k candidates) straight into this rank's
+// record; the O partials stay where they are for head_finalize_fused_kernel<true>.  One thread per (row, sweep).
+__global__ void __launch_bounds__(128) head_reduce_scalars_kernel(const ReduceJobs jobs, int n, int k, const uint8_t* __restrict__ is_out,
+                                                                  float* __restrict__ rec) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n) return;
+  const int i = t / 3, w = t - 3 * i;
+  const ReduceJob& r = jobs.j[w];
+  float acc = 0.f;
+  for (int c = 0; c < r.n_chunks; ++c) acc += r.l_part[(int64_t)c * n + i];
+  rec[(int64_t)(w == 0 ? 0 : 1 + w) * n + i] = acc;
+  if (w == 0) rec[(int64_t)1 * n + i] = 0.f;
+  float tv[KMAX];
+  int32_t ti[KMAX];
+  for (int q = 0; q < KMAX; ++q) {
+    tv[q] = -INFINITY;
+    ti[q] = -1;
+  }
+  if (is_out[i]) {
+    for (int c = 0; c < r.n_chunks; ++c)
+      for (int q = 0; q < k; ++q) {
+        const float v = r.topv_part[((int64_t)c * n + i) * k + q];
+        if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, r.topi_part[((int64_t)c * n + i) * k + q]);
+      }
+  }
+  float* topv = rec + 8 * (int64_t)n;
+  int32_t* topi = reinterpret_cast<int32_t*>(rec + 8 * (int64_t)n + 3 * (int64_t)n * k);
+  for (int q = 0; q < k; ++q) {
+    int32_t id = ti[q];
+    if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
+    topv[((int64_t)w * n + i) * k + q] = tv[q];
+    topi[((int64_t)w * n + i) * k + q] = id;
+  }
+}
+
+// Fast path of the bf16 AM / Arc head: chunk reduction of the three sweeps' partials, the scalar part and dLoss/dp in ONE
+// launch (block = row).  No osum round trip through HBM; replaces reduce + row_coef + finalize.
+//   GATHERED = false (one GPU): the scalars are reduced here from the partials as well;
+//   GATHERED = true (sharded head): the scalars come from the n_ranks gathered records (`rec`, `rec_stride` words apart),
+//     summed in rank order on every rank; O is this rank's partial, so dp is this rank's contribution (reduce-scattered next).
+template <bool GATHERED>
+__global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a, const float* __restrict__ rec,
+                                                                  int64_t rec_stride) {
   const int i = blockIdx.x, n = a.n, D = a.D, k = a.k;
   __shared__ float s_l[3];
   __shared__ float s_tv[3][KMAX];
@@ -661,42 +707,67 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
   __shared__ uint8_t s_wrow[2 * KMAX];
   const bool outl = a.is_out[i];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (w < 3 && lane == 0) {
-    const ReduceJob& r = jobs.j[w];
-    float acc = 0.f;
-    for (int c = 0; c < r.n_chunks; ++c) acc += r.l_part[(int64_t)c * n + i];
-    s_l[w] = acc;
-    float tv[KMAX];
-    int32_t ti[KMAX];
-    for (int q = 0; q < KMAX; ++q) {
-      tv[q] = -INFINITY;
-      ti[q] = -1;
+  if (!GATHERED) {
+    if (w < 3 && lane == 0) {
+      const ReduceJob& r = jobs.j[w];
+      float acc = 0.f;
+      for (int c = 0; c < r.n_chunks; ++c) acc += r.l_part[(int64_t)c * n + i];
+      s_l[w] = acc;
+      float tv[KMAX];
+      int32_t ti[KMAX];
+      for (int q = 0; q < KMAX; ++q) {
+        tv[q] = -INFINITY;
+        ti[q] = -1;
+      }
+      if (outl) {
+        for (int c = 0; c < r.n_chunks; ++c)
+          for (int q = 0; q < k; ++q) {
+            const float v = r.topv_part[((int64_t)c * n + i) * k + q];
+            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, r.topi_part[((int64_t)c * n + i) * k + q]);
+          }
+      }
+      for (int q = 0; q < KMAX; ++q) {
+        int32_t id = ti[q];
+        if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
+        s_tv[w][q] = tv[q];
+        s_ti[w][q] = id;
+      }
     }
-    if (outl) {
-      for (int c = 0; c < r.n_chunks; ++c)
-        for (int q = 0; q < k; ++q) {
-          const float v = r.topv_part[((int64_t)c * n + i) * k + q];
-          if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, r.topi_part[((int64_t)c * n + i) * k + q]);
-        }
-    }
-    for (int q = 0; q < KMAX; ++q) {
-      int32_t id = ti[q];
-      if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
-      s_tv[w][q] = tv[q];
-      s_ti[w][q] = id;
-    }
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
     float loss, cO[2], cT[2];
     int nw;
-    row_coef_math(
-        a, i, 1, [&](int slot) { return slot == 0 ? s_l[0] : (slot >= 2 ? s_l[slot - 1] : 0.f); },
-        [&](int, int set, int q, float& v, int32_t& idx) {
-          v = s_tv[set][q];
-          idx = s_ti[set][q];
-        },
-        loss, cO, cT, nw, s_wslot, s_wrow);
+    if (GATHERED) {
+      const int R = a.n_ranks;
+      row_coef_math(
+          a, i, R,
+          [&](int slot) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc += rec[r * rec_stride + (int64_t)slot * n + i];
+            return acc;
+          },
+          [&](int l) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc += rec[r * rec_stride + (int64_t)(4 + l) * n + i];
+            return acc;
+          },
+          [&](int r, int set, int q, float& v, int32_t& idx) {
+            const float* base = rec + r * rec_stride + 8 * (int64_t)n;
+            const int64_t e = ((int64_t)set * n + i) * k + q;
+            v = base[e];
+            idx = reinterpret_cast<const int32_t*>(base + 3 * (int64_t)n * k)[e];
+          },
+          loss, cO, cT, nw, s_wslot, s_wrow);
+    } else {
+      row_coef_math(
+          a, i, 1, [&](int slot) { return slot == 0 ? s_l[0] : (slot >= 2 ? s_l[slot - 1] : 0.f); }, [&](int l) { return a.tgt[l * n + i]; },
+          [&](int, int set, int q, float& v, int32_t& idx) {
+            v = s_tv[set][q];
+            idx = s_ti[set][q];
+          },
+          loss, cO, cT, nw, s_wslot, s_wrow);
+    }
     a.row_loss[i] = loss;
     s_coef[0] = cO[0];
     s_coef[1] = cO[1];
@@ -1081,13 +1152,10 @@ extern "C" int ffc_head_finalize(ffc_head_t* h, const ffc_head_pass* in, const f
   return head_finalize_impl(h, in, stats, n_ranks_topk, loss_out, dp_out, stream);
 }
 
-static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out, float* dp_out,
-                              void* stream) {
-  FFC_REQUIRE(h && in && stats && loss_out && dp_out, "ffc_head_finalize: NULL argument");
-  FFC_REQUIRE(n_ranks_topk >= 1, "ffc_head_finalize: n_ranks_topk must be >= 1");
+static FinalizeArgs make_finalize_args(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks, float* dp_out) {
   const ffc_head_config& c = h->cfg;
-  cudaStream_t s = (cudaStream_t)stream;
   FinalizeArgs a;
+  memset(&a, 0, sizeof(a));
   a.P = in->p_f32;
   a.qf = in->queue_f32;
   a.qh = (const __nv_bfloat16*)in->queue_bf16;
@@ -1097,12 +1165,14 @@ static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   a.tpos = h->tpos;
   a.is_out = h->is_out;
   a.counts = h->counts + 2 * h->pass_parity;
-  a.lsum = stats->lsum;
-  a.osum = stats->osum;
-  a.tgt = stats->tgt;
-  a.topv = stats->topv;
-  a.topi = stats->topi;
-  a.n_ranks = n_ranks_topk;
+  if (stats) {
+    a.lsum = stats->lsum;
+    a.osum = stats->osum;
+    a.tgt = stats->tgt;
+    a.topv = stats->topv;
+    a.topi = stats->topi;
+  }
+  a.n_ranks = n_ranks;
   a.n = in->n_rows;
   a.D = c.feat_dim;
   a.k = c.topk;
@@ -1114,10 +1184,19 @@ static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   a.fixed_max = fixed_max_of(c);
   a.row_loss = h->row_loss;
   a.dp = dp_out;
+  return a;
+}
+
+static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out, float* dp_out,
+                              void* stream) {
+  FFC_REQUIRE(h && in && stats && loss_out && dp_out, "ffc_head_finalize: NULL argument");
+  FFC_REQUIRE(n_ranks_topk >= 1, "ffc_head_finalize: n_ranks_topk must be >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  const FinalizeArgs a = make_finalize_args(h, in, stats, n_ranks_topk, dp_out);
   if (h->jobs_pending) {       // one-GPU fast path: the sweep left its partials for the fused reduce + finalize
     FFC_REQUIRE(n_ranks_topk == 1, "fused finalize is single-rank");
     h->jobs_pending = 0;
-    head_finalize_fused_kernel<<<a.n, 128, 0, s>>>(*h->jobs, a);
+    head_finalize_fused_kernel<false><<<a.n, 128, 0, s>>>(*h->jobs, a, nullptr, 0);
     FFC_LAUNCH_CHECK();
   } else {
     head_row_coef_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
@@ -1125,6 +1204,48 @@ static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_
     head_finalize_kernel<<<a.n, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
     FFC_LAUNCH_CHECK();
   }
+  head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+// ---- sharded head: per-rank record out of the sweep, finalize from the gathered records ----
+extern "C" int ffc_head_record_words(const ffc_head_config* cfg, int n_rows, int64_t* words_out) {
+  FFC_REQUIRE(cfg && words_out && n_rows >= 0, "ffc_head_record_words: bad arguments");
+  *words_out = record_words(n_rows, cfg->topk);
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_sweep_record(ffc_head_t* h, const ffc_head_pass* in, void* record_out, void* stream) {
+  FFC_REQUIRE(h && in && record_out, "ffc_head_sweep_record: NULL argument");
+  FFC_REQUIRE(h->cfg.precision == FFC_PREC_BF16 && h->cfg.loss_type != FFC_LOSS_SV, "ffc_head_sweep_record: bf16 AM / Arc only");
+  const int n = in->n_rows, k = h->cfg.topk;
+  float* rec = (float*)record_out;
+  ffc_head_stats st;
+  memset(&st, 0, sizeof(st));
+  st.lsum = rec;                       // unused by the deferred path, but head_sweep_impl wants non-NULL statistics
+  st.osum = h->o_part;
+  st.tgt = rec + 4 * (int64_t)n;       // the prep kernel writes the target cosines straight into the record
+  st.topv = rec + 8 * (int64_t)n;
+  st.topi = (int32_t*)(rec + 8 * (int64_t)n + 3 * (int64_t)n * k);
+  int rc = head_sweep_impl(h, in, &st, true, stream);
+  if (rc) return rc;
+  FFC_REQUIRE(h->jobs_pending, "ffc_head_sweep_record: merged sweep path not taken");
+  head_reduce_scalars_kernel<<<(3 * n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*h->jobs, n, k, h->is_out, rec);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_finalize_gathered(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks, int64_t record_stride_words,
+                                          float* loss_out, float* dp_out, void* stream) {
+  FFC_REQUIRE(h && in && records && loss_out && dp_out && n_ranks >= 1, "ffc_head_finalize_gathered: bad arguments");
+  FFC_REQUIRE(h->jobs_pending, "ffc_head_finalize_gathered: no ffc_head_sweep_record pending");
+  FFC_REQUIRE(record_stride_words >= record_words(in->n_rows, h->cfg.topk), "ffc_head_finalize_gathered: record stride too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const FinalizeArgs a = make_finalize_args(h, in, nullptr, n_ranks, dp_out);
+  h->jobs_pending = 0;
+  head_finalize_fused_kernel<true><<<a.n, 128, 0, s>>>(*h->jobs, a, (const float*)records, record_stride_words);
+  FFC_LAUNCH_CHECK();
   head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
   FFC_LAUNCH_CHECK();
   return FFC_OK;

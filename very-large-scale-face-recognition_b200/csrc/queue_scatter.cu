@@ -26,12 +26,12 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
 
 __global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ qf, __nv_bfloat16* __restrict__ qh, const int32_t* __restrict__ rows,
                                                             const int32_t* __restrict__ cols, const float* __restrict__ g, int B, int64_t Q, int D,
-                                                            float* __restrict__ undo) {
+                                                            float* __restrict__ undo, const int32_t* __restrict__ src_row) {
   const int i = blockIdx.x;
   if (cols[i] < 0) return;   // padded position (sharded callers)
   if (later_duplicate(rows, cols, i, B)) return;
   const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
-  const float4* src = reinterpret_cast<const float4*>(g + (int64_t)i * D);
+  const float4* src = reinterpret_cast<const float4*>(g + (int64_t)(src_row ? src_row[i] : i) * D);
   float4* dst = reinterpret_cast<float4*>(qf + off);
   float4* und = undo ? reinterpret_cast<float4*>(undo + (int64_t)i * D) : nullptr;
   for (int v = threadIdx.x; v < D / 4; v += blockDim.x) {
@@ -68,6 +68,69 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
   }
 }
 
+// Stable partition of the gathered gallery keys: the keys this rank owns (floor-mod identity hash, key mod R == rank) first,
+// in global batch order, then the others; order[j] = source position of output j.  One CTA: two passes of a block-wide count.
+__global__ void __launch_bounds__(1024) route_keys_kernel(const int64_t* __restrict__ keys, int n, int R, int rank, int64_t* __restrict__ keys_out,
+                                                          int32_t* __restrict__ order, int32_t* __restrict__ n_mine_out) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base_mine, base_other, total_mine;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto mine_of = [&](int64_t key) {
+    int64_t m = key % R;
+    if (m < 0) m += R;
+    return m == rank;
+  };
+  // pass 1: how many keys are mine
+  int cnt = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) cnt += mine_of(keys[i]) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) warp_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+    total_mine = t;
+    base_mine = 0;
+    base_other = t;
+    *n_mine_out = t;
+  }
+  __syncthreads();
+  // pass 2: stable scatter, 1024 keys per round
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool valid = i < n;
+    const int64_t key = valid ? keys[i] : 0;
+    const bool mine = valid && mine_of(key);
+    const unsigned bm = __ballot_sync(0xffffffffu, mine), bv = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) warp_cnt[warp] = __popc(bm) | (__popc(bv) << 16);
+    __syncthreads();
+    int before_mine = 0, before_valid = 0, all_mine = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = warp_cnt[w];
+      if (w < warp) {
+        before_mine += c & 0xffff;
+        before_valid += c >> 16;
+      }
+      all_mine += c & 0xffff;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    const int my_mine = before_mine + __popc(bm & lt), my_valid = before_valid + __popc(bv & lt);
+    if (valid) {
+      const int dst = mine ? base_mine + my_mine : base_other + (my_valid - my_mine);
+      keys_out[dst] = key;
+      order[dst] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int round_valid = 0;
+      for (int w = 0; w < 32; ++w) round_valid += warp_cnt[w] >> 16;
+      base_mine += all_mine;
+      base_other += round_valid - all_mine;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace ffc
 
 using namespace ffc;
@@ -85,7 +148,32 @@ extern "C" int ffc_queue_scatter(float* queue_f32_dev, void* queue_bf16_dev, con
   FFC_REQUIRE(g_dev != nullptr, "ffc_queue_scatter: g is NULL");
   if (B == 0) return FFC_OK;
   queue_scatter_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, g_dev, B, Q, D,
-                                                             undo_f32_dev);
+                                                             undo_f32_dev, nullptr);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_queue_scatter_indexed(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev, const int32_t* cols_dev,
+                                         const float* g_dev, const int32_t* src_row_dev, int B, int64_t Q, int D, float* undo_f32_dev, void* stream) {
+  int rc = check_scatter_args(queue_f32_dev, rows_dev, cols_dev, B, Q, D);
+  if (rc) return rc;
+  FFC_REQUIRE(g_dev != nullptr && src_row_dev != nullptr, "ffc_queue_scatter_indexed: NULL argument");
+  if (B == 0) return FFC_OK;
+  queue_scatter_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, g_dev, B, Q, D,
+                                                             undo_f32_dev, src_row_dev);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_route_keys(const int64_t* keys_dev, int n, int n_ranks, int rank, int64_t* keys_out_dev, int32_t* order_out_dev,
+                              int32_t* n_mine_out_dev, void* stream) {
+  FFC_REQUIRE(keys_dev && keys_out_dev && order_out_dev && n_mine_out_dev && n >= 0 && n_ranks >= 1 && rank >= 0 && rank < n_ranks,
+              "ffc_route_keys: bad arguments");
+  if (n == 0) {
+    FFC_CUDA(cudaMemsetAsync(n_mine_out_dev, 0, sizeof(int32_t), (cudaStream_t)stream));
+    return FFC_OK;
+  }
+  route_keys_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys_dev, n, n_ranks, rank, keys_out_dev, order_out_dev, n_mine_out_dev);
   FFC_LAUNCH_CHECK();
   return FFC_OK;
 }

@@ -59,7 +59,8 @@ class CudaShardBackend:
             cfg = HeadConfig(n, Ql, q_total, col_offset, D, _capi.LOSS_TYPES[loss_type], scale, margin, topk, _capi.PRECISIONS[precision])
             h = C.c_void_p()
             check(self.lib.ffc_head_create(C.byref(cfg), C.byref(h)))
-            self._h = h
+            self._h, self._cfg = h, cfg
+            self.record_path = precision == 'bf16' and loss_type in ('AM', 'Arc')
         self.sync_mirror()
 
     def __del__(self):
@@ -100,9 +101,21 @@ class CudaShardBackend:
                         n_ones=self.n_ones, cmask=self.cmask, n_dev=n_dev)
         self._n = n
 
-    def scatter(self, g_compact, save_undo):
-        check(self.lib.ffc_queue_scatter(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
-                                         g_compact.data_ptr(), self._n, self.Ql, self.D, self.undo_rows.data_ptr() if save_undo else None, self._s()))
+    def route(self, keys_all, n_ranks, rank):
+        """Stable partition of the gathered gallery keys: this rank's keys first (global batch order).  One launch."""
+        n = keys_all.numel()
+        keys_c = torch.empty_like(keys_all)
+        order = torch.empty(n, dtype=torch.int32, device=self.dev)
+        n_mine = torch.empty(1, dtype=torch.int32, device=self.dev)
+        check(self.lib.ffc_route_keys(keys_all.data_ptr(), n, n_ranks, rank, keys_c.data_ptr(), order.data_ptr(), n_mine.data_ptr(), self._s()))
+        return keys_c, order, n_mine
+
+    def scatter(self, g_all, order, save_undo):
+        """Enqueue this rank's gallery rows straight out of the all-gathered embeddings (row j of the bookkeeping <- g_all[order[j]])."""
+        assert g_all.dtype == torch.float32 and g_all.is_contiguous() and order.dtype == torch.int32
+        check(self.lib.ffc_queue_scatter_indexed(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                                 g_all.data_ptr(), order.data_ptr(), self._n, self.Ql, self.D,
+                                                 self.undo_rows.data_ptr() if save_undo else None, self._s()))
 
     def undo_bookkeeping(self):
         """lru.py:252-255 + ffc.py:256-257: the LRU / queue positions of a rollback pass can be restored as soon as the probe
@@ -123,6 +136,29 @@ class CudaShardBackend:
         red = st['red']
         hs = HeadStats(red.data_ptr(), st['osum'].data_ptr(), red.data_ptr() + 4 * n * 4, st['topv'][slot].data_ptr(), st['topi'][slot].data_ptr())
         return hp, hs
+
+    # -- record path (one all-gather per pass instead of all-reduce + all-gather; see include/ffc_b200.h) --------------------
+    def new_records(self, n, n_ranks):
+        w = C.c_int64()
+        check(self.lib.ffc_head_record_words(C.byref(self._cfg), n, C.byref(w)))
+        return dict(own=torch.empty(w.value, dtype=torch.float32, device=self.dev),
+                    all=torch.empty(n_ranks, w.value, dtype=torch.float32, device=self.dev), words=w.value)
+
+    def _pass_struct(self, p_all, label):
+        return HeadPass(p_all.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), label.data_ptr(), self.ones_list.data_ptr(),
+                        self.n_ones.data_ptr(), self.cmask.data_ptr(), p_all.shape[0])
+
+    def sweep_record(self, p_all, label, rec):
+        hp = self._pass_struct(p_all, label)
+        check(self.lib.ffc_head_sweep_record(self._h, C.byref(hp), rec['own'].data_ptr(), self._s()))
+
+    def finalize_gathered(self, p_all, label, rec, n_ranks):
+        hp = self._pass_struct(p_all, label)
+        dp = torch.empty(p_all.shape[0], self.D, dtype=torch.float32, device=self.dev)
+        loss = torch.empty((), dtype=torch.float32, device=self.dev)
+        check(self.lib.ffc_head_finalize_gathered(self._h, C.byref(hp), rec['all'].data_ptr(), n_ranks, rec['words'], loss.data_ptr(), dp.data_ptr(),
+                                                  self._s()))
+        return loss, dp
 
     def sweep(self, p_all, label, st, rank_slot):
         hp, hs = self._structs(p_all, label, st, rank_slot)
@@ -240,6 +276,25 @@ class ShardedFFCHead:
         l_all = self._all_gather(torch.as_tensor(label).to(device=dev, dtype=torch.int64))
         return e_all, l_all
 
+    def gather_pair(self, x, y, x_label, y_label):
+        """Both sides of the batch in ONE all-gather (NCCL): each rank contributes [x | y | x_label | y_label] as one packed
+        buffer of 4-byte words.  Returns (x_all, xl_all, y_all, yl_all) in global batch order (rank-major)."""
+        if not self._nccl:
+            return self.gather(x, x_label) + self.gather(y, y_label)
+        dev, B, D, R = self.dev, self.B, self.D, self.R
+        assert x.shape == (B, D) and y.shape == (B, D), f'every rank must feed max_batch={B} rows of {D} features'
+        ne = B * D
+        own = torch.empty(2 * ne + 4 * B, dtype=torch.float32, device=dev)
+        own[:ne].view(B, D).copy_(x.detach())
+        own[ne:2 * ne].view(B, D).copy_(y.detach())
+        lab = own[2 * ne:].view(torch.int64)
+        lab[:B].copy_(torch.as_tensor(x_label).reshape(B), non_blocking=True)
+        lab[B:].copy_(torch.as_tensor(y_label).reshape(B), non_blocking=True)
+        buf = torch.empty(R, own.numel(), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(buf, own, group=self.group)
+        labs = buf[:, 2 * ne:].view(torch.int64)                      # [R, 2B]
+        return (buf[:, :ne].reshape(R * B, D), labs[:, :B].reshape(R * B), buf[:, ne:2 * ne].reshape(R * B, D), labs[:, B:].reshape(R * B))
+
     def head_pass(self, p, g, probe_label, gallery_label, commit):
         self._mark('start')
         p_all, pl_all = self.gather(p, probe_label)
@@ -251,8 +306,7 @@ class ShardedFFCHead:
         """ffc.py:264-267 on embeddings without autograd glue: both passes share ONE all-gather of (x, x_label) and
         (y, y_label), since the commit pass only swaps the roles.  Returns (loss, dLoss/dx, dLoss/dy) for the rank's rows."""
         self._mark('start')
-        x_all, xl_all = self.gather(x, x_label)
-        y_all, yl_all = self.gather(y, y_label)
+        x_all, xl_all, y_all, yl_all = self.gather_pair(x, y, x_label, y_label)
         self._mark('all_gather')
         ctx_rb = self._bookkeep(xl_all, yl_all, False, 0)
         if self._nccl and self._side is not None:
@@ -286,10 +340,13 @@ class ShardedFFCHead:
         be = self.backend
         if hasattr(be, 'use_set'):
             be.use_set(set_idx)
-        mine = self.shard_of(gl_all) == self.rank
-        order = torch.argsort((~mine).to(torch.int8), stable=True)
-        n_mine = mine.sum().to(torch.int32).reshape(1)
-        keys_c = gl_all[order].contiguous()
+        if hasattr(be, 'route'):
+            keys_c, order, n_mine = be.route(gl_all, self.R, self.rank)
+        else:
+            mine = self.shard_of(gl_all) == self.rank
+            order = torch.argsort((~mine).to(torch.int8), stable=True)
+            n_mine = mine.sum().to(torch.int32).reshape(1)
+            keys_c = gl_all[order].contiguous()
         self._mark('route')
         be.assign(keys_c, n_mine, journal=not commit)
         self._mark('lru_assign')
@@ -307,9 +364,21 @@ class ShardedFFCHead:
         n = p_all.shape[0]
         if hasattr(be, 'use_set'):
             be.use_set(ctx['set'])
-        be.scatter(g_all[ctx['order']].contiguous(), save_undo=not commit)
+        be.scatter(g_all, ctx['order'], save_undo=not commit)
         self._mark('scatter')
         label = ctx['label']
+        if getattr(be, 'record_path', False):
+            # one record per rank and pass, one all-gather, finalize straight from the sweep partials
+            rec = self._stats.get(('rec', n))
+            if rec is None:
+                rec = self._stats[('rec', n)] = be.new_records(n, R)
+            be.sweep_record(p_all, label, rec)
+            self._mark('sweep')
+            dist.all_gather_into_tensor(rec['all'], rec['own'], group=self.group)
+            self._mark('stat_exchange')
+            loss, dp_part = be.finalize_gathered(p_all, label, rec, R)
+            self._mark('finalize')
+            return self._finish_tail(be, dp_part, loss, label, ctx, commit)
         st = self._stats.get(n)
         if st is None:
             st = self._stats[n] = be.new_stats(n, R)
@@ -332,6 +401,9 @@ class ShardedFFCHead:
         self._mark('stat_exchange')
         loss, dp_part = be.finalize(p_all, label, st, R)
         self._mark('finalize')
+        return self._finish_tail(be, dp_part, loss, label, ctx, commit)
+
+    def _finish_tail(self, be, dp_part, loss, label, ctx, commit):
         dp = self._reduce_scatter(dp_part)
         self._mark('reduce_scatter')
         if not commit:
