@@ -244,6 +244,57 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// Hard-negative top-k (ffc.py:86-92) over 16 raw cosines v[BASE .. BASE+16) of one row (= lane), columns col0 .. col0+15.
+// Branch-free register list of integer keys: only POSITIVE cosines can contribute (clip(.., 0) zeroes the rest and their
+// gradient), positive floats order like their int32 bit patterns, and the low 4 mantissa bits carry the column's index inside
+// the 16-column chunk (value error 2^-19).  tk[] descending keys (0 = empty), tc[] first column of the chunk a key came from.
+// Warp-collective: all lanes run the same code; a lane with a candidate (key above its k-th) extracts its largest remaining
+// key per round until no lane has any left.
+template <int BASE, int NV>
+__device__ __forceinline__ void topk_scan16(const uint32_t (&v)[NV], uint32_t excl, int col0, bool outl, int k, int (&tk)[KMAX], int (&tc)[KMAX],
+                                            int& kth) {
+  int key[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    key[c] = (int)((v[BASE + c] & 0xfffffff0u) | (uint32_t)c);
+    if ((excl >> c) & 1u) key[c] = 0;
+  }
+  int bound = 0x7fffffff;      // keys >= bound were already extracted in this chunk
+  while (true) {
+    int mx = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) mx = max(mx, key[c] < bound ? key[c] : 0);
+    const bool has = outl && mx > kth;
+    if (!__any_sync(0xffffffffu, has)) break;
+    if (has) {
+      int xk = mx, xc = col0;
+#pragma unroll
+      for (int r = 0; r < KMAX; ++r) {
+        if (r < k) {
+          const bool pgt = xk > tk[r];
+          const int nk = pgt ? xk : tk[r], nc = pgt ? xc : tc[r];
+          xk = pgt ? tk[r] : xk;
+          xc = pgt ? tc[r] : xc;
+          tk[r] = nk;
+          tc[r] = nc;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < KMAX; ++r)
+        if (r == k - 1) kth = tk[r];
+      bound = mx;
+    } else {
+      bound = 0;               // this lane is done with the chunk
+    }
+  }
+}
+
 #ifndef FFC_SM100_DEBUG_BUILD
 #define FFC_SM100_DEBUG_BUILD 0     // 1: honour Sm100Params::debug (bottleneck isolation, see tools/sweep_modes.py)
 #endif
@@ -508,10 +559,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const float a2 = prm.a2, b2 = prm.b2;
       const int k = prm.k;
       float lsum = 0.f;
-      // Hard-negative top-k (ffc.py:86-92) as a branch-free register list of integer keys: only POSITIVE cosines can
-      // contribute (clip(.., 0) zeroes the rest and their gradient), positive floats order like their int32 bit
-      // patterns, and the low 4 mantissa bits carry the column's index inside its 16-column chunk (value error 2^-19).
-      // tk[] descending keys (0 = empty), tc[] first column of the chunk the key came from.
+      // hard-negative top-k state of this row (see topk_scan16)
       int tk[KMAX], tc[KMAX];
 #pragma unroll
       for (int q = 0; q < KMAX; ++q) {
@@ -519,6 +567,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         tc[q] = -1;
       }
       int kth = 0;
+      float pthr = __uint_as_float(__float_as_uint(ex2f(-b2)) & 0xffff0000u);    // p~ of cosine 0, rounded down to bf16
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
       // tile i uses S buffer i % NSB and P~ buffer i % NPB; NEPI == NPB, so this warpgroup always writes P~ buffer g
@@ -547,10 +596,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
         // A tile is "clean" for this warp when no column is excluded (no `ones` column, no row's target, not the
         // ragged tail) and no row takes part in the top-k: then the chunk loop is pure ld -> ex2 -> pack -> st.async.
-        const bool clean = !warp_out && !__any_sync(0xffffffffu, (cm.x | cm.y | cm.z | cm.w) != 0u || (unsigned)(tcol - j0) < (unsigned)BN) &&
+        // (Without SV, p~ is monotonic in the cosine, so outlier rows stay on the fast loop: a chunk can only hold a top-k
+        // candidate if the maximum of its packed p~ reaches the row's threshold -- one bf16x2 max tree per 32 columns.)
+        const bool clean = (!SV || !warp_out) && !__any_sync(0xffffffffu, (cm.x | cm.y | cm.z | cm.w) != 0u || (unsigned)(tcol - j0) < (unsigned)BN) &&
                            (int64_t)j0 + BN <= n_cols;
         if (clean) {
           float l0 = 0.f, l1 = 0.f;
+          if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)0xfffffff0), a2, -b2))) & 0xffff0000u);
 #pragma unroll 1
           for (int cc = 0; cc < BN / 32; ++cc) {
             uint32_t v[32];
@@ -583,6 +635,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               l1 += p1;
               pk[c >> 1] = pack_bf16(g0, g1);
             }
+            if (!SV && warp_out) {
+              uint32_t m = pk[0];
+#pragma unroll
+              for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
+              const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
+              if (__any_sync(0xffffffffu, outl && mf >= pthr)) {
+                const int kth0 = kth;
+                topk_scan16<0, 32>(v, 0u, j0 + cc * 32, outl, k, tk, tc, kth);
+                topk_scan16<16, 32>(v, 0u, j0 + cc * 32 + 16, outl, k, tk, tc, kth);
+                // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
+                if (kth != kth0) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)0xfffffff0), a2, -b2))) & 0xffff0000u);
+              }
+            }
             // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
             if (!dbg_noHand) {
 #pragma unroll
@@ -607,44 +672,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             excl |= nv <= 0 ? 0xffffu : (0xffffu << nv) & 0xffffu;
           }
           const bool slow = __any_sync(0xffffffffu, excl != 0u);
-          // hard-negative top-k on the raw cosines of outlier rows: all lanes run the same code; a lane with a
-          // candidate (key above its k-th) extracts its largest remaining key per round until no lane has any left
-          if (warp_out) {
-            int key[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              key[c] = (int)((v[c] & 0xfffffff0u) | (uint32_t)c);
-              if (slow && ((excl >> c) & 1u)) key[c] = 0;
-            }
-            int bound = 0x7fffffff;      // keys >= bound were already extracted in this chunk
-            while (true) {
-              int mx = 0;
-#pragma unroll
-              for (int c = 0; c < 16; ++c) mx = max(mx, key[c] < bound ? key[c] : 0);
-              const bool has = outl && mx > kth;
-              if (!__any_sync(0xffffffffu, has)) break;
-              if (has) {
-                int xk = mx, xc = col0;
-#pragma unroll
-                for (int r = 0; r < KMAX; ++r) {
-                  if (r < k) {
-                    const bool pgt = xk > tk[r];
-                    const int nk = pgt ? xk : tk[r], nc = pgt ? xc : tc[r];
-                    xk = pgt ? tk[r] : xk;
-                    xc = pgt ? tc[r] : xc;
-                    tk[r] = nk;
-                    tc[r] = nc;
-                  }
-                }
-#pragma unroll
-                for (int r = 0; r < KMAX; ++r)
-                  if (r == k - 1) kth = tk[r];
-                bound = mx;
-              } else {
-                bound = 0;               // this lane is done with the chunk
-              }
-            }
-          }
+          // hard-negative top-k on the raw cosines of outlier rows
+          if (warp_out) topk_scan16<0, 16>(v, slow ? excl : 0u, col0, outl, k, tk, tc, kth);
           uint32_t pk[8];
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
