@@ -32,14 +32,19 @@ namespace ffc {
 constexpr int BM = 128;            // probe rows per item
 constexpr int BN = 128;            // queue rows per tile
 constexpr int KC = 64;             // bf16 elements per 128-byte swizzle row
+#ifndef FFC_P_TMEM
+#define FFC_P_TMEM 1     // 1: the probe tile P is the TMEM A operand of GEMM-1 (tcgen05.mma TS form); 0: P resident in shared memory (SS form)
+#endif
 #ifndef FFC_NS1
-#define FFC_NS1 6
+#define FFC_NS1 (FFC_P_TMEM ? 12 : 6)
 #endif
 #ifndef FFC_JB
 #define FFC_JB 32
 #endif
 constexpr int NS1 = FFC_NS1;       // S-CTA W K-chunk stages (16 KB each)
-constexpr int NSB = 4;             // S accumulators in the S-CTA's TMEM (4 x 128 columns)
+constexpr bool P_TMEM = FFC_P_TMEM != 0;
+constexpr int NSB = P_TMEM ? 2 : 4; // S accumulators in the S-CTA's TMEM (128 columns each); with P in TMEM: S0 S1 | P (D/2 columns at 256)
+constexpr int P_TMEM_COL = 256;
 constexpr int NPB = 3;             // P~ buffers in the O-CTA's shared memory
 constexpr int JB = FFC_JB;         // queue rows per O-CTA W stage
 constexpr int NEPI = 3;             // epilogue warpgroups in the S-CTA (tiles are dealt round-robin)
@@ -57,7 +62,8 @@ constexpr int PT_BYTES = BM * BN * 2;       // 32768 per P~ buffer
 struct Bars {   // all in the first 1024 bytes
   uint64_t p_full;
   uint64_t w_full[NS1], w_empty[NS1];
-  uint64_t s_full[NSB], s_empty[NSB];
+  uint64_t s_full[NEPI];           // one per epilogue warpgroup (NOT per S buffer): each is waited by one warpgroup, in order
+  uint64_t s_empty[NSB];
   uint64_t pt_empty[NPB];          // S-CTA side: P~ buffer b may be overwritten (signalled by the peer's tcgen05.commit)
   uint64_t w2_full[8], w2_empty[8];
   uint64_t pt_full[NPB];           // O-CTA side: P~ buffer b is complete (st.async complete_tx, 32 KB per tile)
@@ -146,6 +152,26 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+      "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+      "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -352,6 +378,7 @@ struct SubSweep {
 };
 struct Sm100Params {
   int n_rows;
+  const __nv_bfloat16* p16;   // [n_rows, D] probe rows (bf16), loaded straight into TMEM when P_TMEM
   const uint8_t* is_out;
   float a2, b2;       // p~ = 2^(a2 * z - b2)
   int k;
@@ -369,7 +396,7 @@ struct SweepShape {
   static constexpr int NS2 = NS2_RAW > 8 ? 8 : (NS2_RAW < 2 ? 2 : NS2_RAW);
   static constexpr int N2 = D < 256 ? D : 256;               // GEMM-2 instruction N
   static constexpr int NHALF = (D + 255) / 256;              // GEMM-2 instructions per K step
-  static constexpr size_t SMEM_S = OFF_DATA + (size_t)NKC * CHUNK1_BYTES + (size_t)NS1 * CHUNK1_BYTES;
+  static constexpr size_t SMEM_S = OFF_DATA + (P_TMEM ? 0 : (size_t)NKC * CHUNK1_BYTES) + (size_t)NS1 * CHUNK1_BYTES;
   static constexpr size_t SMEM_O = OFF_DATA + NPB * (size_t)PT_BYTES + (size_t)NS2 * STAGE2_BYTES;
   static constexpr size_t SMEM = (SMEM_S > SMEM_O ? SMEM_S : SMEM_O) + 1024;   // slack for the 1024-byte alignment of the base
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
@@ -412,20 +439,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     FFC_STAMP_NS(6);
   }
   unsigned char* sP = smem + OFF_DATA;                         // S-CTA
-  unsigned char* sW1 = sP + NKC * CHUNK1_BYTES;                // S-CTA
+  unsigned char* sW1 = sP + (P_TMEM ? 0 : NKC * CHUNK1_BYTES);   // S-CTA (P lives in TMEM when P_TMEM)
   unsigned char* sPt = smem + OFF_DATA;                        // O-CTA
   unsigned char* sW2 = sPt + NPB * PT_BYTES;                   // O-CTA
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars.p_full, 1);
+    mbar_init(&bars.p_full, P_TMEM ? 4 : 1);
     for (int i = 0; i < NS1; ++i) {
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
     }
-    for (int i = 0; i < NSB; ++i) {
-      mbar_init(&bars.s_full[i], 1);
-      mbar_init(&bars.s_empty[i], 4);
-    }
+    for (int i = 0; i < NEPI; ++i) mbar_init(&bars.s_full[i], 1);
+    for (int i = 0; i < NSB; ++i) mbar_init(&bars.s_empty[i], 4);
     for (int i = 0; i < NPB; ++i) {
       mbar_init(&bars.pt_empty[i], 1);
       mbar_init(&bars.pt_full[i], 1);
@@ -440,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   }
   if (warp == 2) {
     // S-CTA: NSB x 128 columns of S; O-CTA: D columns of O (power of two >= 32)
-    const uint32_t ncols = rank == 0 ? (uint32_t)(NSB * BN) : (uint32_t)(D < 32 ? 32 : D);
+    const uint32_t ncols = rank == 0 ? 512u : (uint32_t)(D < 32 ? 32 : D);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -455,12 +480,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
     if (warp == 0) {
       // ---- TMA producer (converged warp, one elected lane issues) ----
       if (n_tiles > 0 && !dbg_noS) {
-        if (elect_one()) {
-          mbar_expect_tx(&bars.p_full, (uint32_t)(NKC * CHUNK1_BYTES));
+        if (!P_TMEM) {
+          if (elect_one()) {
+            mbar_expect_tx(&bars.p_full, (uint32_t)(NKC * CHUNK1_BYTES));
 #pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&map_p, &bars.p_full, sP + kc * CHUNK1_BYTES, kc * KC, row0);
+            for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&map_p, &bars.p_full, sP + kc * CHUNK1_BYTES, kc * KC, row0);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         int stage = 0;
         uint32_t ph = 0;
         FFC_PROF_DECL(prof_tma);
@@ -498,7 +525,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         FFC_PROF_DECL(prof_a);
         FFC_PROF_DECL(prof_b);
         FFC_PROF_DECL(prof_c);
-        for (int i = 0; i < n_tiles; ++i) {
+        int wg = 0;      // epilogue warpgroup of tile i (i % NEPI): its s_full barrier is signalled
+        for (int i = 0; i < n_tiles; ++i, wg = (wg + 1 == NEPI ? 0 : wg + 1)) {
           const int sb = i & (NSB - 1);
           FFC_PROF_T(q0);
           mbar_wait(&bars.s_empty[sb], ((uint32_t)(i / NSB) & 1) ^ 1);
@@ -506,7 +534,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           FFC_PROF_T(q1);
           FFC_PROF_ADD(prof_a, q0, q1);
           if (dbg_noS) {
-            if (elect_one()) mbar_arrive(&bars.s_full[sb]);
+            if (elect_one()) mbar_arrive(&bars.s_full[wg]);
             __syncwarp();
             continue;
           }
@@ -521,12 +549,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             FFC_PROF_T(q3);
             FFC_PROF_ADD(prof_b, q2, q3);
             if (elect_one()) {
-              const uint64_t ad = a0 + (uint64_t)(kc * (CHUNK1_BYTES >> 4));
               const uint64_t bd = b0 + (uint64_t)(stage * (CHUNK1_BYTES >> 4));
+              if (P_TMEM) {
+                // A = P[128 x 16] from TMEM: lane = probe row, 8 columns (two bf16 per column) per K = 16 step
+                const uint32_t ta = tmem_base + (uint32_t)(P_TMEM_COL + kc * (KC / 2));
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) tc_mma(tmem_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+                for (int k = 0; k < KC / 16; ++k) tc_mma_ts(tmem_s, ta + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+              } else {
+                const uint64_t ad = a0 + (uint64_t)(kc * (CHUNK1_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) tc_mma(tmem_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+              }
               if (!dbg_noTma) tc_commit(&bars.w_empty[stage]);
-              if (kc == NKC - 1) tc_commit(&bars.s_full[sb]);
+              if (kc == NKC - 1) tc_commit(&bars.s_full[wg]);
             }
             __syncwarp();
             FFC_PROF_T(q4);
@@ -574,6 +609,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       static_assert(NEPI == NPB, "epilogue warpgroups and P~ buffers are paired");
       const int pb = g;
       uint32_t pt_use = 0;
+      if (P_TMEM && g == 0 && n_tiles > 0 && !dbg_noS) {
+        // probe tile -> TMEM (the A operand of every GEMM-1 of this item): thread = row, 32 columns (64 bf16, 128 bytes) per store
+        const uint4* src = reinterpret_cast<const uint4*>(prm.p16 + (int64_t)(row_ok ? row : 0) * D);
+        const uint32_t tp = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)P_TMEM_COL;
+#pragma unroll 1
+        for (int c0 = 0; c0 < D / 2; c0 += 32) {
+          uint32_t v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 t = row_ok ? __ldg(src + c0 / 4 + q) : make_uint4(0u, 0u, 0u, 0u);
+            v[4 * q] = t.x;
+            v[4 * q + 1] = t.y;
+            v[4 * q + 2] = t.z;
+            v[4 * q + 3] = t.w;
+          }
+          tc_st32(tp + (uint32_t)c0, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full);
+      }
       FFC_PROF_DECL(prof_e0);
       FFC_PROF_DECL(prof_e1);
       FFC_PROF_DECL(prof_e2);
@@ -584,7 +641,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         uint4 cm = make_uint4(0u, 0u, 0u, 0u);
         if (sw.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(sw.cmask + (j0 >> 5)));
         FFC_PROF_T(e0);
-        mbar_wait(&bars.s_full[sb], (uint32_t)(i / NSB) & 1);
+        // s_full is per warpgroup: tile i is this warpgroup's pt_use-th tile.  (Per-buffer barriers would be waited by
+        // different warpgroups in turn; with fewer S buffers than warpgroups + 1 a slow warpgroup gets lapped by a phase and
+        // a parity wait two phases behind never returns.)
+        mbar_wait(&bars.s_full[g], pt_use & 1);
         tc_fence_after();
         FFC_PROF_T(e1);
         if (!dbg_noHand) mbar_wait(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
@@ -611,6 +671,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               for (int c = 0; c < 32; ++c) v[c] = 0u;
             } else {
               tc_ld32(tmem_s + cc * 32, v);
+            }
+            if (cc == BN / 32 - 1) {      // S buffer sb is in registers now: a later tile's MMA may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
             }
             uint32_t pk[16];
 #pragma unroll
@@ -662,6 +727,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         for (int cc = 0; cc < BN / 16; ++cc) {
           uint32_t v[16];
           tc_ld16(tmem_s + cc * 16, v);
+          if (cc == BN / 16 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
+          }
           const int col0 = j0 + cc * 16;
           const uint32_t cw = (cc >> 1) == 0 ? cm.x : (cc >> 1) == 1 ? cm.y : (cc >> 1) == 2 ? cm.z : cm.w;
           uint32_t excl = (cw >> ((cc & 1) * 16)) & 0xffffu;
@@ -704,10 +774,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                           pk[4 * q + 3]);
           }
         }
-        // S buffer sb may be overwritten by a later tile's MMA
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
         FFC_PROF_T(e3);
         FFC_PROF_ADD(prof_e2, e2, e3);
       }
@@ -945,7 +1011,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   if (threadIdx.x == 0) FFC_STAMP(4);
   cluster_sync_all();     // the peer may still signal into this CTA's shared memory until here
   if (warp == 2) {
-    const uint32_t ncols = rank == 0 ? (uint32_t)(NSB * BN) : (uint32_t)(D < 32 ? 32 : D);
+    const uint32_t ncols = rank == 0 ? 512u : (uint32_t)(D < 32 ? 32 : D);
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
   if (threadIdx.x == 0) {
@@ -1102,6 +1168,7 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
   Sm100Params p;
   memset(&p, 0, sizeof(p));
   p.n_rows = a.n_rows;
+  p.p16 = a.P_bf16;
   p.is_out = a.is_out;
   p.a2 = a.scale * LOG2E;
   p.b2 = a.fixed_max * LOG2E;
