@@ -30,6 +30,7 @@ struct ffc_head {
   int32_t* tcol;               // [max_rows]  target column in the main sweep (local) or -1
   int32_t* tpos;               // [max_rows]  target position in ones_list or -1
   uint8_t* is_out;             // [max_rows]
+  int32_t* kth_shared;         // [max_rows] hard-negative threshold shared by the column chunks of the tcgen05 sweep
   float* thr;                  // [2][max_rows]
   int32_t* counts;             // [2][2] n_pos, n_out, double-buffered by pass parity
   int pass_parity;
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(128) head_prep_fused_kernel(const float* __res
                                                               const int32_t* __restrict__ ones_list, const int32_t* __restrict__ n_ones_p, int max_rows,
                                                               float* __restrict__ side_f32, __nv_bfloat16* __restrict__ side_bf16,
                                                               int32_t* __restrict__ tcol, int32_t* __restrict__ tpos, uint8_t* __restrict__ is_out,
-                                                              int32_t* counts_cur, int32_t* counts_next, float margin, float* __restrict__ tgt,
-                                                              float* __restrict__ thr) {
+                                                              int32_t* __restrict__ kth_shared, int32_t* counts_cur, int32_t* counts_next, float margin,
+                                                              float* __restrict__ tgt, float* __restrict__ thr) {
   const int b = blockIdx.x;
   const int no = *n_ones_p;
   __shared__ int found;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(128) head_prep_fused_kernel(const float* __res
       tcol[i] = tc;
       tpos[i] = fpos;
       is_out[i] = lab < 0;
+      kth_shared[i] = 0;
       atomicAdd(&counts_cur[lab < 0 ? 1 : 0], 1);
     }
     // bf16 probe row + target cosines: tgt[0] = p . queue[0][t], tgt[1] = p . (t in C ? queue[1][t] : queue[0][t])
@@ -903,6 +905,7 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_CUDA(cudaMalloc(&h->tcol, R * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->tpos, R * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->is_out, R));
+  FFC_CUDA(cudaMalloc(&h->kth_shared, R * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->thr, 2 * R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->counts, 4 * sizeof(int32_t)));
   FFC_CUDA(cudaMemset(h->counts, 0, 4 * sizeof(int32_t)));
@@ -930,6 +933,7 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
   cudaFree(h->tcol);
   cudaFree(h->tpos);
   cudaFree(h->is_out);
+  cudaFree(h->kth_shared);
   cudaFree(h->thr);
   cudaFree(h->counts);
   cudaFree(h->row_loss);
@@ -1083,11 +1087,11 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
     const int grid = std::min<int>(c.max_rows, (n + 127) & ~127);
     if (bf16)
       head_prep_fused_kernel<true><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
-                                                        in->n_ones, c.max_rows, nullptr, h->side_bf16, h->tcol, h->tpos, h->is_out, cur, nxt, c.margin,
+                                                        in->n_ones, c.max_rows, nullptr, h->side_bf16, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
                                                         out->tgt, sv ? h->thr : nullptr);
     else
       head_prep_fused_kernel<false><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
-                                                         in->n_ones, c.max_rows, h->side_f32, nullptr, h->tcol, h->tpos, h->is_out, cur, nxt, c.margin,
+                                                         in->n_ones, c.max_rows, h->side_f32, nullptr, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
                                                          out->tgt, sv ? h->thr : nullptr);
     FFC_LAUNCH_CHECK();
   }
@@ -1099,6 +1103,7 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
   a.n_rows = n;
   a.D = D;
   a.is_out = h->is_out;
+  a.kth_shared = h->kth_shared;
   a.scale = c.scale;
   a.fixed_max = fixed_max_of(c);
   a.sv = sv;

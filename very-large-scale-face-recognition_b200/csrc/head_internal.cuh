@@ -25,6 +25,7 @@ struct SweepArgs {
   const uint32_t* cmask;         // bit per column or NULL
   const float* thr;              // [n_rows] or NULL (=> +inf)
   const uint8_t* is_out;         // [n_rows] 1 if the row takes part in the hard-negative top-k
+  int32_t* kth_shared;           // [n_rows] zero-initialised scratch: threshold shared by the column chunks (tcgen05 path; never NULL there)
   float scale;                   // s
   float fixed_max;               // M
   int sv;                        // SV transform enabled

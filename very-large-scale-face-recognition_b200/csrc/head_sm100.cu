@@ -36,7 +36,7 @@ constexpr int KC = 64;             // bf16 elements per 128-byte swizzle row
 #define FFC_P_TMEM 1     // 1: the probe tile P is the TMEM A operand of GEMM-1 (tcgen05.mma TS form); 0: P resident in shared memory (SS form)
 #endif
 #ifndef FFC_NS1
-#define FFC_NS1 (FFC_P_TMEM ? 12 : 6)
+#define FFC_NS1 (FFC_P_TMEM ? 12 : 5)
 #endif
 #ifndef FFC_JB
 #define FFC_JB 32
@@ -270,6 +270,8 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+constexpr uint32_t TOPK_VAL_MASK = 0xffffffe0u;   // top-k keys: cosine bits with the low 5 mantissa bits replaced by the column's index in its chunk
+
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -279,16 +281,31 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 // Hard-negative top-k (ffc.py:86-92) over 16 raw cosines v[BASE .. BASE+16) of one row (= lane), columns col0 .. col0+15.
 // Branch-free register list of integer keys: only POSITIVE cosines can contribute (clip(.., 0) zeroes the rest and their
 // gradient), positive floats order like their int32 bit patterns, and the low 4 mantissa bits carry the column's index inside
-// the 16-column chunk (value error 2^-19).  tk[] descending keys (0 = empty), tc[] first column of the chunk a key came from.
-// Warp-collective: all lanes run the same code; a lane with a candidate (key above its k-th) extracts its largest remaining
-// key per round until no lane has any left.
+// the chunk (5 bits: up to 32 columns; value error 2^-18).  tk[] descending keys (0 = empty), tc[] first column of the chunk a key came from.
+// Warp-collective: all lanes run the same code; a lane with a candidate (key above its threshold `kth`) extracts its largest
+// remaining key per round until no lane has any left.  `kfloor` is the row's threshold shared by the column chunks (below).
+// sorted insertion of one key into the branch-free register list (the caller has checked xk > kth)
+__device__ __forceinline__ void topk_insert_key(int xk, int xc, int k, int (&tk)[KMAX], int (&tc)[KMAX]) {
+#pragma unroll
+  for (int r = 0; r < KMAX; ++r) {
+    if (r < k) {
+      const bool pgt = xk > tk[r];
+      const int nk = pgt ? xk : tk[r], nc = pgt ? xc : tc[r];
+      xk = pgt ? tk[r] : xk;
+      xc = pgt ? tc[r] : xc;
+      tk[r] = nk;
+      tc[r] = nc;
+    }
+  }
+}
+
 template <int BASE, int NV>
 __device__ __forceinline__ void topk_scan16(const uint32_t (&v)[NV], uint32_t excl, int col0, bool outl, int k, int (&tk)[KMAX], int (&tc)[KMAX],
-                                            int& kth) {
+                                            int& kth, int kfloor) {
   int key[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    key[c] = (int)((v[BASE + c] & 0xfffffff0u) | (uint32_t)c);
+    key[c] = (int)((v[BASE + c] & TOPK_VAL_MASK) | (uint32_t)c);
     if ((excl >> c) & 1u) key[c] = 0;
   }
   int bound = 0x7fffffff;      // keys >= bound were already extracted in this chunk
@@ -313,7 +330,7 @@ __device__ __forceinline__ void topk_scan16(const uint32_t (&v)[NV], uint32_t ex
       }
 #pragma unroll
       for (int r = 0; r < KMAX; ++r)
-        if (r == k - 1) kth = tk[r];
+        if (r == k - 1) kth = max(tk[r], kfloor);     // own k-th, or the row's shared threshold if that is higher
       bound = mx;
     } else {
       bound = 0;               // this lane is done with the chunk
@@ -380,6 +397,7 @@ struct Sm100Params {
   int n_rows;
   const __nv_bfloat16* p16;   // [n_rows, D] probe rows (bf16), loaded straight into TMEM when P_TMEM
   const uint8_t* is_out;
+  int32_t* kth_shared;        // [n_rows] shared hard-negative threshold (integer key), zeroed by the prep kernel
   float a2, b2;       // p~ = 2^(a2 * z - b2)
   int k;
   int debug;   // bottleneck isolation BITMASK, only in FFC_SM100_DEBUG_BUILD builds; results are WRONG when any bit is set:
@@ -396,7 +414,7 @@ struct SweepShape {
   static constexpr int NS2 = NS2_RAW > 8 ? 8 : (NS2_RAW < 2 ? 2 : NS2_RAW);
   static constexpr int N2 = D < 256 ? D : 256;               // GEMM-2 instruction N
   static constexpr int NHALF = (D + 255) / 256;              // GEMM-2 instructions per K step
-  static constexpr size_t SMEM_S = OFF_DATA + (P_TMEM ? 0 : (size_t)NKC * CHUNK1_BYTES) + (size_t)NS1 * CHUNK1_BYTES;
+  static constexpr size_t SMEM_S = OFF_DATA + (P_TMEM ? 0 : (size_t)NKC * CHUNK1_BYTES) + (size_t)NS1 * CHUNK1_BYTES + NEPI * 4 * 128;   // + top-k scan staging
   static constexpr size_t SMEM_O = OFF_DATA + NPB * (size_t)PT_BYTES + (size_t)NS2 * STAGE2_BYTES;
   static constexpr size_t SMEM = (SMEM_S > SMEM_O ? SMEM_S : SMEM_O) + 1024;   // slack for the 1024-byte alignment of the base
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
@@ -602,6 +620,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         tc[q] = -1;
       }
       int kth = 0;
+      // Threshold shared by the work items of the same probe rows (one per column chunk): the k-th largest cosine any of them
+      // has seen so far is a lower bound of the row's final k-th, so nothing at or below it can enter the merged top-k.  Each
+      // item publishes its own k-th (atomicMax on the integer key) and picks the maximum up at every tile: the candidate rate
+      // of an item falls as if it had seen all chunks' columns.  Main sweep only (the side sets merge per loss).
+      uint32_t* scan_stage = reinterpret_cast<uint32_t*>(sW1 + NS1 * CHUNK1_BYTES) + (warp - 4) * 32;   // 128 bytes per epilogue warp
+      int32_t* kshare = (sidx == 0 && outl) ? prm.kth_shared + row : nullptr;
+      int kfloor = 0, kpub = 0;
       float pthr = __uint_as_float(__float_as_uint(ex2f(-b2)) & 0xffff0000u);    // p~ of cosine 0, rounded down to bf16
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
@@ -634,12 +659,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       FFC_PROF_DECL(prof_e0);
       FFC_PROF_DECL(prof_e1);
       FFC_PROF_DECL(prof_e2);
+      FFC_PROF_DECL(prof_trig);
       for (int i = g; i < n_tiles; i += NEPI, ++pt_use) {
         const int sb = i & (NSB - 1);
         const int j0 = (t_begin + i) * BN;
         // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
         uint4 cm = make_uint4(0u, 0u, 0u, 0u);
         if (sw.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(sw.cmask + (j0 >> 5)));
+        int kshared = 0;
+        if (kshare) kshared = __ldcg(kshare);
         FFC_PROF_T(e0);
         // s_full is per warpgroup: tile i is this warpgroup's pt_use-th tile.  (Per-buffer barriers would be waited by
         // different warpgroups in turn; with fewer S buffers than warpgroups + 1 a slow warpgroup gets lapped by a phase and
@@ -658,11 +686,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         // ragged tail) and no row takes part in the top-k: then the chunk loop is pure ld -> ex2 -> pack -> st.async.
         // (Without SV, p~ is monotonic in the cosine, so outlier rows stay on the fast loop: a chunk can only hold a top-k
         // candidate if the maximum of its packed p~ reaches the row's threshold -- one bf16x2 max tree per 32 columns.)
+        kfloor = max(kfloor, kshared);
+        kth = max(kth, kfloor);
         const bool clean = (!SV || !warp_out) && !__any_sync(0xffffffffu, (cm.x | cm.y | cm.z | cm.w) != 0u || (unsigned)(tcol - j0) < (unsigned)BN) &&
                            (int64_t)j0 + BN <= n_cols;
         if (clean) {
           float l0 = 0.f, l1 = 0.f;
-          if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)0xfffffff0), a2, -b2))) & 0xffff0000u);
+          if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
 #pragma unroll 1
           for (int cc = 0; cc < BN / 32; ++cc) {
             uint32_t v[32];
@@ -705,12 +735,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll
               for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
               const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
-              if (__any_sync(0xffffffffu, outl && mf >= pthr)) {
-                const int kth0 = kth;
-                topk_scan16<0, 32>(v, 0u, j0 + cc * 32, outl, k, tk, tc, kth);
-                topk_scan16<16, 32>(v, 0u, j0 + cc * 32 + 16, outl, k, tk, tc, kth);
+              unsigned cand = __ballot_sync(0xffffffffu, outl && mf >= pthr);
+              if (cand) {
+                FFC_PROF_ADD(prof_trig, 0, 1);
+                // Usually ONE lane (row) has a candidate: its 32 cosines go through shared memory so that the 32 lanes test one
+                // column each; the row's lane then inserts the (usually single) hit.  ~40 instructions instead of a 32-key scan.
+                if (__popc(cand) > 4) {      // many rows at once (the first tiles of an item): the per-lane scan is cheaper
+                  topk_scan16<0, 32>(v, 0u, j0 + cc * 32, outl, k, tk, tc, kth, kfloor);
+                  topk_scan16<16, 32>(v, 0u, j0 + cc * 32 + 16, outl, k, tk, tc, kth, kfloor);
+                  cand = 0u;
+                }
+                while (cand) {
+                  const int L = __ffs(cand) - 1;
+                  cand &= cand - 1;
+                  if (lane == L) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scan_stage + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                  }
+                  __syncwarp();
+                  const int key = (int)((scan_stage[lane] & TOPK_VAL_MASK) | (uint32_t)lane);
+                  const int kthL = __shfl_sync(0xffffffffu, kth, L);
+                  unsigned hits = __ballot_sync(0xffffffffu, key > kthL);
+                  while (hits) {
+                    const int c = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int kc = __shfl_sync(0xffffffffu, key, c);
+                    if (lane == L && kc > kth) {
+                      topk_insert_key(kc, j0 + cc * 32, k, tk, tc);
+#pragma unroll
+                      for (int r = 0; r < KMAX; ++r)
+                        if (r == k - 1) kth = max(tk[r], kfloor);
+                    }
+                  }
+                  __syncwarp();
+                }
                 // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
-                if (kth != kth0) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)0xfffffff0), a2, -b2))) & 0xffff0000u);
+                pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
               }
             }
             // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
@@ -743,7 +803,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           }
           const bool slow = __any_sync(0xffffffffu, excl != 0u);
           // hard-negative top-k on the raw cosines of outlier rows
-          if (warp_out) topk_scan16<0, 16>(v, slow ? excl : 0u, col0, outl, k, tk, tc, kth);
+          if (warp_out) topk_scan16<0, 16>(v, slow ? excl : 0u, col0, outl, k, tk, tc, kth, kfloor);
           uint32_t pk[8];
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
@@ -774,6 +834,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                           pk[4 * q + 3]);
           }
         }
+        if (kshare) {      // publish this item's own k-th when it has risen
+          int kown = 0;
+#pragma unroll
+          for (int r = 0; r < KMAX; ++r)
+            if (r == k - 1) kown = tk[r];
+          if (kown > kpub) {
+            atomicMax(kshare, kown);
+            kpub = kown;
+          }
+        }
         FFC_PROF_T(e3);
         FFC_PROF_ADD(prof_e2, e2, e3);
       }
@@ -781,6 +851,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         FFC_PROF_STORE(3, prof_e0);
         FFC_PROF_STORE(4, prof_e1);
         FFC_PROF_STORE(5, prof_e2);
+        FFC_PROF_STORE(7, prof_trig);
       }
       // ---- per-row partials: combine the three warpgroups through shared memory ----
       float* stage_v = reinterpret_cast<float*>(sW1);                             // [2][128][KMAX] (W ring is idle now)
@@ -794,8 +865,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll
       for (int q = 0; q < KMAX; ++q) {
         const bool live = tk[q] > 0;
-        tv[q] = live ? __int_as_float(tk[q] & (int)0xfffffff0) : -INFINITY;
-        ti[q] = live ? tc[q] + (tk[q] & 15) : -1;
+        tv[q] = live ? __int_as_float(tk[q] & (int)TOPK_VAL_MASK) : -INFINITY;
+        ti[q] = live ? tc[q] + (tk[q] & 31) : -1;
       }
       if (g >= 1) {
         stage_l[(g - 1) * BM + r_local] = lsum;
@@ -1137,16 +1208,16 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
     static long long hp[1024][8];
     cudaMemcpyFromSymbol(hp, g_sweep_prof, sizeof(hp));
     for (int role = 0; role < 2; ++role) {
-      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       int cnt = 0;
       for (int i = role; i < n; i += 2, ++cnt)
-        for (int k = 0; k < 7; ++k) acc[k] += (double)hp[i][k];
+        for (int k = 0; k < 8; ++k) acc[k] += (double)hp[i][k];
       const double nt = (double)p.sub[0].tiles_per_chunk;
       fprintf(fo, "  %s-CTA cycles/tile: MMA warp waits for %s %.0f, waits for W %.0f, issues %.0f | TMA producer waits %.0f", role ? "O" : "S",
               role ? "P~" : "a free S buffer", acc[0] / cnt / nt, acc[1] / cnt / nt, acc[2] / cnt / nt, acc[6] / cnt / nt);
       if (role == 0)
-        fprintf(fo, " | epilogue warp (1 of 3 warpgroups; per tile of the CTA): waits for S %.0f, waits for a free P~ buffer %.0f, works %.0f", acc[3] / cnt / nt,
-                acc[4] / cnt / nt, acc[5] / cnt / nt);
+        fprintf(fo, " | epilogue warp (1 of 3 warpgroups; per tile of the CTA): waits for S %.0f, waits for a free P~ buffer %.0f, works %.0f; top-k scans in %.1f%% of its 32-column chunks", acc[3] / cnt / nt,
+                acc[4] / cnt / nt, acc[5] / cnt / nt, 100.0 * acc[7] / cnt / (nt / 3.0 * 4.0));
       fprintf(fo, "\n");
     }
     if (fo != stderr) fclose(fo);
@@ -1170,6 +1241,7 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
   p.n_rows = a.n_rows;
   p.p16 = a.P_bf16;
   p.is_out = a.is_out;
+  p.kth_shared = a.kth_shared;
   p.a2 = a.scale * LOG2E;
   p.b2 = a.fixed_max * LOG2E;
   p.k = a.k;
