@@ -124,6 +124,21 @@ int ffc_route_keys(const int64_t* keys_dev, int n, int n_ranks, int rank, int64_
 int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
                       const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
                       void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Gallery-network EMA (replaces ffc.py:139-145 _momentum_update_gallery), SURVEY 8(f) rank 1.
+ * One launch over all parameter tensors: the caller splits every fp32 tensor into chunks of at most
+ * ffc_ema_chunk_elems() elements and passes the chunk table (device memory).  g = g*m + p*one_minus_m with the
+ * reference's rounding (two fp32 multiplies, one add, no FMA): bit-identical to the eager expression.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ffc_ema_chunk {
+  float* gallery;       /* updated in place */
+  const float* probe;
+  int32_t n;            /* elements in this chunk (<= ffc_ema_chunk_elems()) */
+  int32_t pad;
+} ffc_ema_chunk;
+int ffc_ema_chunk_elems(void);
+int ffc_ema_update(const ffc_ema_chunk* table_dev, int n_chunks, float m, float one_minus_m, void* stream);
+
 /* fp32 -> bf16 mirror of n contiguous elements (queue initialisation / checkpoint load). */
 int ffc_cast_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n, void* stream);
 

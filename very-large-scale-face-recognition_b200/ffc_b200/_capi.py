@@ -60,6 +60,8 @@ PROTOTYPES = {
     'ffc_head_finalize_gathered': (c_int, [c_void_p, C.POINTER(HeadPass), c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'ffc_queue_scatter_indexed': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     'ffc_route_keys': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ffc_ema_chunk_elems': (c_int, []),
+    'ffc_ema_update': (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),
     'ffc_head_set_timing': (c_int, [c_void_p, c_int]),
     'ffc_head_get_timing': (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64)]),
     'ffc_head_stats_bytes': (c_int, [C.POINTER(HeadConfig), c_int, C.POINTER(c_int64)]),
