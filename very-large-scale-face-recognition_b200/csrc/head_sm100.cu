@@ -682,132 +682,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
         const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
         const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
-        // A tile is "clean" for this warp when no column is excluded (no `ones` column, no row's target, not the
-        // ragged tail) and no row takes part in the top-k: then the chunk loop is pure ld -> ex2 -> pack -> st.async.
-        // (Without SV, p~ is monotonic in the cosine, so outlier rows stay on the fast loop: a chunk can only hold a top-k
-        // candidate if the maximum of its packed p~ reaches the row's threshold -- one bf16x2 max tree per 32 columns.)
+        // One loop over the tile's four 32-column chunks.  Exclusions (a `ones` column, the row's target, the ragged tail) are
+        // decided per CHUNK and warp-uniformly: only chunks that hold one pay for the per-element test, the others are pure
+        // ld -> ex2 -> pack -> st.async.  (At 8-way shard shapes ~60 % of the TILES hold a `ones` column, but only ~20 % of
+        // the chunks.)
         kfloor = max(kfloor, kshared);
         kth = max(kth, kfloor);
-        const bool clean = (!SV || !warp_out) && !__any_sync(0xffffffffu, (cm.x | cm.y | cm.z | cm.w) != 0u || (unsigned)(tcol - j0) < (unsigned)BN) &&
-                           (int64_t)j0 + BN <= n_cols;
-        if (clean) {
-          float l0 = 0.f, l1 = 0.f;
-          if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+        if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
-          for (int cc = 0; cc < BN / 32; ++cc) {
-            uint32_t v[32];
-            if (dbg_noEpi) {
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t v[32];
+          if (dbg_noEpi) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) v[c] = 0u;
-            } else {
-              tc_ld32(tmem_s + cc * 32, v);
-            }
-            if (cc == BN / 32 - 1) {      // S buffer sb is in registers now: a later tile's MMA may overwrite it
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
-            }
-            uint32_t pk[16];
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              if (dbg_noEpi) {
-                pk[c >> 1] = 0u;
-                continue;
-              }
-              const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
-              float p0, p1, g0, g1;
-              if (SV) {
-                const bool m0 = x0 > thr, m1 = x1 > thr;
-                p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
-                p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
-                g0 = m0 ? p0 * SV_T : p0;
-                g1 = m1 ? p1 * SV_T : p1;
-              } else {
-                p0 = g0 = ex2f(fmaf(x0, a2, -b2));
-                p1 = g1 = ex2f(fmaf(x1, a2, -b2));
-              }
-              l0 += p0;
-              l1 += p1;
-              pk[c >> 1] = pack_bf16(g0, g1);
-            }
-            if (!SV && warp_out) {
-              uint32_t m = pk[0];
-#pragma unroll
-              for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
-              const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
-              unsigned cand = __ballot_sync(0xffffffffu, outl && mf >= pthr);
-              if (cand) {
-                FFC_PROF_ADD(prof_trig, 0, 1);
-                // Usually ONE lane (row) has a candidate: its 32 cosines go through shared memory so that the 32 lanes test one
-                // column each; the row's lane then inserts the (usually single) hit.  ~40 instructions instead of a 32-key scan.
-                if (__popc(cand) > 4) {      // many rows at once (the first tiles of an item): the per-lane scan is cheaper
-                  topk_scan16<0, 32>(v, 0u, j0 + cc * 32, outl, k, tk, tc, kth, kfloor);
-                  topk_scan16<16, 32>(v, 0u, j0 + cc * 32 + 16, outl, k, tk, tc, kth, kfloor);
-                  cand = 0u;
-                }
-                while (cand) {
-                  const int L = __ffs(cand) - 1;
-                  cand &= cand - 1;
-                  if (lane == L) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scan_stage + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                  }
-                  __syncwarp();
-                  const int key = (int)((scan_stage[lane] & TOPK_VAL_MASK) | (uint32_t)lane);
-                  const int kthL = __shfl_sync(0xffffffffu, kth, L);
-                  unsigned hits = __ballot_sync(0xffffffffu, key > kthL);
-                  while (hits) {
-                    const int c = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const int kc = __shfl_sync(0xffffffffu, key, c);
-                    if (lane == L && kc > kth) {
-                      topk_insert_key(kc, j0 + cc * 32, k, tk, tc);
-#pragma unroll
-                      for (int r = 0; r < KMAX; ++r)
-                        if (r == k - 1) kth = max(tk[r], kfloor);
-                    }
-                  }
-                  __syncwarp();
-                }
-                // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
-                pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
-              }
-            }
-            // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
-            if (!dbg_noHand) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 4 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
-                            pk[4 * q + 3]);
-            }
+            for (int c = 0; c < 32; ++c) v[c] = 0u;
+          } else {
+            tc_ld32(tmem_s + cc * 32, v);
           }
-          lsum += l0 + l1;
-        } else
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 16; ++cc) {
-          uint32_t v[16];
-          tc_ld16(tmem_s + cc * 16, v);
-          if (cc == BN / 16 - 1) {
+          if (cc == BN / 32 - 1) {      // S buffer sb is in registers now: a later tile's MMA may overwrite it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
           }
-          const int col0 = j0 + cc * 16;
-          const uint32_t cw = (cc >> 1) == 0 ? cm.x : (cc >> 1) == 1 ? cm.y : (cc >> 1) == 2 ? cm.z : cm.w;
-          uint32_t excl = (cw >> ((cc & 1) * 16)) & 0xffffu;
+          const int col0 = j0 + cc * 32;
+          uint32_t excl = cc == 0 ? cm.x : cc == 1 ? cm.y : cc == 2 ? cm.z : cm.w;
           const int trel = tcol - col0;
-          if ((unsigned)trel < 16u) excl |= 1u << trel;
-          if ((int64_t)col0 + 16 > n_cols) {
+          if ((unsigned)trel < 32u) excl |= 1u << trel;
+          if ((int64_t)col0 + 32 > n_cols) {
             const int nv = (int)(n_cols - col0);   // valid columns in this chunk (may be <= 0)
-            excl |= nv <= 0 ? 0xffffu : (0xffffu << nv) & 0xffffu;
+            excl |= nv <= 0 ? 0xffffffffu : (0xffffffffu << nv);
           }
           const bool slow = __any_sync(0xffffffffu, excl != 0u);
-          // hard-negative top-k on the raw cosines of outlier rows
-          if (warp_out) topk_scan16<0, 16>(v, slow ? excl : 0u, col0, outl, k, tk, tc, kth, kfloor);
-          uint32_t pk[8];
+          uint32_t pk[16];
 #pragma unroll
-          for (int c = 0; c < 16; c += 2) {
-            float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
+          for (int c = 0; c < 32; c += 2) {
+            if (dbg_noEpi) {
+              pk[c >> 1] = 0u;
+              continue;
+            }
+            const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
             float p0, p1, g0, g1;
             if (SV) {
               const bool m0 = x0 > thr, m1 = x1 > thr;
@@ -823,17 +736,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               if ((excl >> c) & 1u) p0 = g0 = 0.f;
               if ((excl >> (c + 1)) & 1u) p1 = g1 = 0.f;
             }
-            lsum += p0 + p1;
+            l0 += p0;
+            l1 += p1;
             pk[c >> 1] = pack_bf16(g0, g1);
           }
-          // P~[r_local][cc*16 .. +16) = 2 pieces of 16 bytes (st.async, 32 KB per tile in total on pt_full[pb])
+          // ---- hard-negative top-k on the raw cosines of outlier rows ----
+          if (SV) {
+            if (warp_out) {
+              topk_scan16<0, 32>(v, excl & 0xffffu, col0, outl, k, tk, tc, kth, kfloor);
+              topk_scan16<16, 32>(v, excl >> 16, col0 + 16, outl, k, tk, tc, kth, kfloor);
+            }
+          } else if (warp_out) {
+            // Without SV, p~ is monotonic in the cosine: the chunk can only hold a candidate if the maximum of its packed p~ (one
+            // bf16x2 max tree; excluded columns are 0) reaches the row's threshold mapped to p~ space.
+            uint32_t m = pk[0];
+#pragma unroll
+            for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
+            const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
+            unsigned cand = __ballot_sync(0xffffffffu, outl && mf >= pthr);
+            if (cand) {
+              FFC_PROF_ADD(prof_trig, 0, 1);
+              if (__popc(cand) > 4) {      // many rows at once (the first tiles of an item): the per-lane scan is cheaper
+                topk_scan16<0, 32>(v, excl & 0xffffu, col0, outl, k, tk, tc, kth, kfloor);
+                topk_scan16<16, 32>(v, excl >> 16, col0 + 16, outl, k, tk, tc, kth, kfloor);
+                cand = 0u;
+              }
+              // Usually ONE lane (row) has a candidate: its 32 cosines go through shared memory so that the 32 lanes test one
+              // column each; the row's lane then inserts the (usually single) hit.  ~40 instructions instead of a 32-key scan.
+              while (cand) {
+                const int L = __ffs(cand) - 1;
+                cand &= cand - 1;
+                if (lane == L) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scan_stage + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                __syncwarp();
+                const uint32_t exclL = __shfl_sync(0xffffffffu, excl, L);
+                const int key = ((exclL >> lane) & 1u) ? 0 : (int)((scan_stage[lane] & TOPK_VAL_MASK) | (uint32_t)lane);
+                const int kthL = __shfl_sync(0xffffffffu, kth, L);
+                unsigned hits = __ballot_sync(0xffffffffu, key > kthL);
+                while (hits) {
+                  const int c = __ffs(hits) - 1;
+                  hits &= hits - 1;
+                  const int kc = __shfl_sync(0xffffffffu, key, c);
+                  if (lane == L && kc > kth) {
+                    topk_insert_key(kc, col0, k, tk, tc);
+#pragma unroll
+                    for (int r = 0; r < KMAX; ++r)
+                      if (r == k - 1) kth = max(tk[r], kfloor);
+                  }
+                }
+                __syncwarp();
+              }
+              // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
+              pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+            }
+          }
+          // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
           if (!dbg_noHand) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-              st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 2 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
+            for (int q = 0; q < 4; ++q)
+              st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 4 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
                           pk[4 * q + 3]);
           }
         }
+        lsum += l0 + l1;
         if (kshare) {      // publish this item's own k-th when it has risen
           int kown = 0;
 #pragma unroll
