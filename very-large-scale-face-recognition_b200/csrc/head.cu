@@ -699,22 +699,25 @@ __global__ void __launch_bounds__(128) head_reduce_scalars_kernel(const ReduceJo
 template <bool GATHERED>
 __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a, const float* __restrict__ rec,
                                                                   int64_t rec_stride) {
-  const int i = blockIdx.x, n = a.n, D = a.D, k = a.k;
-  __shared__ float s_l[3];
-  __shared__ float s_tv[3][KMAX];
-  __shared__ int32_t s_ti[3][KMAX];
-  __shared__ float s_coef[4];
-  __shared__ int s_nw;
-  __shared__ int32_t s_wslot[2 * KMAX];
-  __shared__ uint8_t s_wrow[2 * KMAX];
-  const bool outl = a.is_out[i];
+  // One WARP per row (4 rows per block): the scalar part is ~1000 dependent fp64 operations on one lane (16 us on this part's
+  // fp64 pipe), so rows must run side by side -- with a block per row 8 192 rows took 3.5 waves of that latency (130 us).
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + w, n = a.n, D = a.D, k = a.k;
+  if (i >= n) return;
+  __shared__ float s_l[4][3];
+  __shared__ float s_tv[4][3][KMAX];
+  __shared__ int32_t s_ti[4][3][KMAX];
+  __shared__ float s_coef[4][4];
+  __shared__ int s_nw[4];
+  __shared__ int32_t s_wslot[4][2 * KMAX];
+  __shared__ uint8_t s_wrow[4][2 * KMAX];
+  const bool outl = a.is_out[i];
   if (!GATHERED) {
-    if (w < 3 && lane == 0) {
-      const ReduceJob& r = jobs.j[w];
+    if (lane < 3) {
+      const ReduceJob& r = jobs.j[lane];
       float acc = 0.f;
       for (int c = 0; c < r.n_chunks; ++c) acc += r.l_part[(int64_t)c * n + i];
-      s_l[w] = acc;
+      s_l[w][lane] = acc;
       float tv[KMAX];
       int32_t ti[KMAX];
       for (int q = 0; q < KMAX; ++q) {
@@ -731,13 +734,13 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
       for (int q = 0; q < KMAX; ++q) {
         int32_t id = ti[q];
         if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
-        s_tv[w][q] = tv[q];
-        s_ti[w][q] = id;
+        s_tv[w][lane][q] = tv[q];
+        s_ti[w][lane][q] = id;
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     float loss, cO[2], cT[2];
     int nw;
     if (GATHERED) {
@@ -760,29 +763,29 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
             v = base[e];
             idx = reinterpret_cast<const int32_t*>(base + 3 * (int64_t)n * k)[e];
           },
-          loss, cO, cT, nw, s_wslot, s_wrow);
+          loss, cO, cT, nw, s_wslot[w], s_wrow[w]);
     } else {
       row_coef_math(
-          a, i, 1, [&](int slot) { return slot == 0 ? s_l[0] : (slot >= 2 ? s_l[slot - 1] : 0.f); }, [&](int l) { return a.tgt[l * n + i]; },
+          a, i, 1, [&](int slot) { return slot == 0 ? s_l[w][0] : (slot >= 2 ? s_l[w][slot - 1] : 0.f); }, [&](int l) { return a.tgt[l * n + i]; },
           [&](int, int set, int q, float& v, int32_t& idx) {
-            v = s_tv[set][q];
-            idx = s_ti[set][q];
+            v = s_tv[w][set][q];
+            idx = s_ti[w][set][q];
           },
-          loss, cO, cT, nw, s_wslot, s_wrow);
+          loss, cO, cT, nw, s_wslot[w], s_wrow[w]);
     }
     a.row_loss[i] = loss;
-    s_coef[0] = cO[0];
-    s_coef[1] = cO[1];
-    s_coef[2] = cT[0];
-    s_coef[3] = cT[1];
-    s_nw = nw;
+    s_coef[w][0] = cO[0];
+    s_coef[w][1] = cO[1];
+    s_coef[w][2] = cT[0];
+    s_coef[w][3] = cT[1];
+    s_nw[w] = nw;
   }
-  __syncthreads();
-  const float cO0 = s_coef[0], cO1 = s_coef[1], cT0 = s_coef[2], cT1 = s_coef[3];
+  __syncwarp();
+  const float cO0 = s_coef[w][0], cO1 = s_coef[w][1], cT0 = s_coef[w][2], cT1 = s_coef[w][3];
   const int32_t tc = a.tcol[i];
   const int trow2 = (a.tpos[i] >= 0) ? 1 : 0;
-  const int nw = s_nw;
-  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+  const int nw = s_nw[w];
+  for (int d = lane * 4; d < D; d += 32 * 4) {
     float g[4] = {0.f, 0.f, 0.f, 0.f};
     if (!outl) {
       float o[3][4];
@@ -809,10 +812,10 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
       }
     } else {
       for (int x = 0; x < nw; ++x) {
-        const int64_t loc = (int64_t)s_wslot[x] - a.col_offset;
+        const int64_t loc = (int64_t)s_wslot[w][x] - a.col_offset;
         if (loc >= 0 && loc < a.q_local) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) g[e] += cO0 * w_elem(a, s_wrow[x], loc, d + e);
+          for (int e = 0; e < 4; ++e) g[e] += cO0 * w_elem(a, s_wrow[w][x], loc, d + e);
         }
       }
     }
@@ -1201,7 +1204,7 @@ static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   if (h->jobs_pending) {       // one-GPU fast path: the sweep left its partials for the fused reduce + finalize
     FFC_REQUIRE(n_ranks_topk == 1, "fused finalize is single-rank");
     h->jobs_pending = 0;
-    head_finalize_fused_kernel<false><<<a.n, 128, 0, s>>>(*h->jobs, a, nullptr, 0);
+    head_finalize_fused_kernel<false><<<(a.n + 3) / 4, 128, 0, s>>>(*h->jobs, a, nullptr, 0);
     FFC_LAUNCH_CHECK();
   } else {
     head_row_coef_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
@@ -1249,7 +1252,7 @@ extern "C" int ffc_head_finalize_gathered(ffc_head_t* h, const ffc_head_pass* in
   cudaStream_t s = (cudaStream_t)stream;
   const FinalizeArgs a = make_finalize_args(h, in, nullptr, n_ranks, dp_out);
   h->jobs_pending = 0;
-  head_finalize_fused_kernel<true><<<a.n, 128, 0, s>>>(*h->jobs, a, (const float*)records, record_stride_words);
+  head_finalize_fused_kernel<true><<<(a.n + 3) / 4, 128, 0, s>>>(*h->jobs, a, (const float*)records, record_stride_words);
   FFC_LAUNCH_CHECK();
   head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
   FFC_LAUNCH_CHECK();
