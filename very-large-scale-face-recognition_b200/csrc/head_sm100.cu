@@ -4,19 +4,20 @@
 // CLUSTER OF TWO CTAs with different roles, because at D = 512 the fp32 gradient accumulator
 // O[128 x 512] alone fills the 512 TMEM columns of one SM:
 //
-//   CTA rank 0, "S-CTA":  S = P . W_tile^T        (tcgen05.mma, M=128 N=128 K=D, A = P resident in
-//                          smem, B = W K-chunks streamed by TMA);  8 epilogue warps read S from TMEM,
-//                          apply exclusions / SV transform, p~ = 2^(a*cos - b), accumulate the softmax
-//                          denominator and the running top-k, and store p~ as bf16 straight into the
-//                          peer CTA's shared memory (st.shared::cluster) in the K-major SWIZZLE_128B
-//                          layout the second GEMM reads.
-//   CTA rank 1, "O-CTA":  O += P~ . W_tile          (tcgen05.mma, M=128 N<=256 per instruction, K=128
-//                          queue rows per tile, A = P~ from smem, B = the same W tile streamed by TMA
-//                          and read MN-major);  O stays in TMEM for the whole item and is written once.
+//   CTA rank 0, "S-CTA":  S = P . W_tile^T        (tcgen05.mma TS form, M=128 N=128 K=D: A = the probe tile P resident in
+//                          TMEM, B = W K-chunks streamed by TMA through a 12-stage ring);  12 epilogue warps read S from
+//                          TMEM, apply exclusions / SV transform, p~ = 2^(a*cos - b), accumulate the softmax denominator and
+//                          the running top-k, and store p~ as bf16 straight into the peer CTA's shared memory (st.async) in
+//                          the interleaved K-major layout the second GEMM reads (512 contiguous bytes per warp store).
+//   CTA rank 1, "O-CTA":  O += P~ . W_tile          (tcgen05.mma SS form, M=128 N<=256 per instruction, K=128 queue rows per
+//                          tile, A = P~ from smem, B = the same W tile, one 3-D TMA box per stage, read MN-major);  O stays
+//                          in TMEM for the whole item and is written once.
 //
-// Executed tensor FLOPs == algorithmic FLOPs (4 * rows * cols * D): no recompute, no B x Q logits.
-// Synchronisation is all mbarriers: TMA -> MMA (full/empty rings), MMA -> epilogue (tcgen05.commit),
-// epilogue -> peer MMA (st.async complete_tx on the peer's mbarrier), peer MMA -> epilogue (multicast tcgen05.commit).
+// Executed tensor FLOPs == algorithmic FLOPs (4 * rows * cols * D): no recompute, no B x Q logits.  One launch carries the
+// main sweep and the two side sweeps of a pass.  Every MMA / TMA warp runs converged with one elected lane issuing.
+// Synchronisation is all mbarriers: TMA -> MMA (full/empty rings), MMA -> epilogue (tcgen05.commit, one barrier per
+// epilogue warpgroup), epilogue -> peer hand-off warp (st.async complete_tx on the peer's mbarrier) -> peer MMA,
+// peer MMA -> epilogue (multicast tcgen05.commit).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -186,15 +187,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -212,31 +204,11 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32
                "r"(c), "r"(d), "r"(mbar)
                : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 // tcgen05.commit that arrives on the barrier at the same offset in the CTAs of `cta_mask`
 __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
-}
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {   // long waits: back off instead of spinning
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    asm volatile("nanosleep.u32 2000;");
-  }
 }
 
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): SWIZZLE_128B, version 1
