@@ -54,9 +54,13 @@ constexpr int CHUNK1_BYTES = BN * KC * 2;   // 16384
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ---- shared memory map (same for both roles; 1024-byte aligned base) ----
-// [0, 1024)                 barriers, tmem base, small staging
-// S-CTA: [1024, +D/64*16K)  P tile (K-major SW128 chunks)      then NS1 x 16 KB W chunk ring
-// O-CTA: [1024, +96K)       P~ buffers 3 x 32 KB               then NS2 x (D/64 * 4 KB) W stage ring
+// [0, 1024)                 barriers, tmem base
+// S-CTA: [1024, ...)        NS1 x 16 KB W chunk ring (K-major SW128), then 12 x 128 B top-k scan staging
+//                           (with FFC_P_TMEM=0 the P tile, D/64 x 16 KB, sits in front of the ring)
+// O-CTA: [1024, +96K)       P~ buffers 3 x 32 KB (interleaved K-major), then NS2 x (D/64 * 4 KB) W stage ring
+// ---- tensor memory (512 columns per SM) ----
+// S-CTA: [0, 256) two S accumulators, [256, 256 + D/2) the probe tile P as packed bf16 pairs (lane = row)
+// O-CTA: [0, D) the fp32 gradient accumulator O
 constexpr int OFF_DATA = 1024;
 constexpr int PT_BYTES = BM * BN * 2;       // 32768 per P~ buffer
 

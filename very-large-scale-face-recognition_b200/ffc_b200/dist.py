@@ -55,7 +55,6 @@ class CudaShardBackend:
                                ones_list=torch.empty(n, **i32), n_ones=torch.zeros(1, **i32)) for _ in range(2)]
             self.use_set(0)
             self.undo_rows = torch.empty(n, D, **f32)
-            self.loss_buf = torch.zeros(1, **f32)
             cfg = HeadConfig(n, Ql, q_total, col_offset, D, _capi.LOSS_TYPES[loss_type], scale, margin, topk, _capi.PRECISIONS[precision])
             h = C.c_void_p()
             check(self.lib.ffc_head_create(C.byref(cfg), C.byref(h)))

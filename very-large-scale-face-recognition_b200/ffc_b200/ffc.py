@@ -149,7 +149,6 @@ class FFCHead(Module):
                            n_ones=torch.zeros(1, **i32), cmask=torch.zeros((Q + 31) // 32 + 1, **i32), free=None) for _ in range(2)]
         self._use_set(0)
         self.undo_rows = torch.empty(R, D, **f32)
-        self.loss_buf = torch.zeros(1, **f32)
         self.stats = dict(lsum=torch.empty(4, R, **f32), osum=torch.empty(4, R, D, **f32), tgt=torch.empty(4, R, **f32),
                           topv=torch.empty(3, R, k, **f32), topi=torch.empty(3, R, k, **i32))
 
