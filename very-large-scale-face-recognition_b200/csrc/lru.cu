@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(256) lru_lookup_kernel(const int64_t* __restri
 // resolve: one CTA replays the batch
 // ------------------------------------------------------------------------------------------------
 struct ResolveSmem {
+  int32_t ones0, ones1;     // n_ones before / after this launch (R6)
+  int32_t ones_pad[2];
   int64_t pkey[NB];
   int64_t nkey[NN];
   int64_t npos[NN];
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_
     S.lh[c] = -1;
     S.firstocc[c] = 0x7fffffff;
   }
+  if (tid == 0 && a.ones_list) S.ones0 = *reinterpret_cast<volatile int32_t*>(a.n_ones);
   int64_t key = 0;
   int32_t s0 = -1;
   if (tid < n) {
@@ -636,6 +639,25 @@ __global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_
       if (last != HS && !(S.nflags[last] & F_TOUCHED)) nt = S.npos[last];
       if (nt > head) nt = head;
       st->tail = nt;
+    }
+  }
+  // R6: `ones` is a set (ffc.py:170/226 ones_idx), but the list is appended with atomics in arrival order; sort this launch's
+  // segment by slot so that the list -- and with it the gather / summation order of the side sweeps -- is run-to-run deterministic
+  if (a.ones_list) {
+    __syncthreads();                              // all R4 appends of this (single) CTA are done
+    if (tid == 0) S.ones1 = *reinterpret_cast<volatile int32_t*>(a.n_ones);
+    __syncthreads();
+    const int n0 = S.ones0, len = S.ones1 - n0;   // len <= n <= NT
+    int32_t mine = 0;
+    if (tid < len) {
+      mine = *reinterpret_cast<volatile int32_t*>(a.ones_list + n0 + tid);
+      S.lh[tid] = mine;                           // the local hash is dead by now: scratch
+    }
+    __syncthreads();
+    if (tid < len) {
+      int rank = 0;
+      for (int j = 0; j < len; ++j) rank += S.lh[j] < mine ? 1 : 0;     // slots are distinct
+      a.ones_list[n0 + rank] = mine;
     }
   }
 }
