@@ -139,6 +139,49 @@ typedef struct ffc_ema_chunk {
 int ffc_ema_chunk_elems(void);
 int ffc_ema_update(const ffc_ema_chunk* table_dev, int n_chunks, float m, float one_minus_m, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backbone tail -> head hand-off, SURVEY 8(f) rank 3 (replaces the last two operations of every reference backbone:
+ * `F.normalize(self.features(x))`, features = nn.BatchNorm1d(feat_dim, eps=1e-05) -- resnet_arcface.py:99,151,
+ * resnet_std.py:201-202; plain `F.normalize(x)` in mobilefacenet_def.py:113-114 -- and their autograd backward).
+ * The unit-norm fp32 rows the head consumes (ffc_head_pass.p_f32, ffc_queue_scatter's g) are written with a row stride,
+ * so they can land directly in a packed staging buffer (the sharded head's all-gather input).
+ * ---------------------------------------------------------------------------------------------- */
+#define FFC_TAIL_NORMALIZE 0 /* p = x / max(||x||_2, 1e-12)                                       */
+#define FFC_TAIL_BN_EVAL 1   /* BatchNorm1d with the running statistics (module.eval()), then normalise  */
+#define FFC_TAIL_BN_TRAIN 2  /* BatchNorm1d with batch statistics (module.train()): running_mean / running_var are
+                                updated as torch does (momentum, unbiased variance), then normalise      */
+
+typedef struct ffc_tail_args {
+  const float* x;        /* [n_rows, feat_dim] fp32, contiguous: the backbone's last linear output; must not alias p */
+  float* p;              /* [n_rows] rows of feat_dim floats, p_stride floats apart: unit-norm output (input of backward) */
+  int64_t p_stride;
+  float* inv_norm;       /* [n_rows]: 1 / max(||y||, 1e-12), written by forward, read by backward */
+  int32_t n_rows;
+  int32_t feat_dim;
+  int32_t mode;          /* FFC_TAIL_* */
+  float eps;             /* BatchNorm1d eps (1e-05 in the reference) */
+  float momentum;        /* running-statistics factor of this step (0.1 default; 1/num_batches_tracked when the
+                            module's momentum is None) */
+  const float* gamma;    /* [feat_dim] BatchNorm1d weight, NULL = 1 */
+  const float* beta;     /* [feat_dim] BatchNorm1d bias, NULL = 0 */
+  float* running_mean;   /* [feat_dim]; read in BN_EVAL, updated in BN_TRAIN (NULL = not tracked) */
+  float* running_var;
+  float* save_mean;      /* [feat_dim] statistics used by this call (BN modes): written by forward, read by backward */
+  float* save_invstd;
+  void* workspace;       /* BN modes: ffc_tail_workspace_bytes() bytes, 16-byte aligned, zero-filled once before its first use (calls
+                            leave it reusable); one workspace must not be shared by calls that may run concurrently */
+  int64_t workspace_bytes;
+} ffc_tail_args;
+
+int ffc_tail_workspace_bytes(int n_rows, int feat_dim, int64_t* bytes_out);
+/* 1 launch (NORMALIZE) or 2 (BN modes). */
+int ffc_tail_forward(const ffc_tail_args* a, void* stream);
+/* Backward of ffc_tail_forward for the same `a` (x, p, inv_norm, save_* unchanged since forward): dp_dev rows dp_stride floats
+ * apart; dx_dev [n_rows, feat_dim] contiguous.  dgamma_dev / dbeta_dev ([feat_dim], overwritten, either may be NULL) are the
+ * BatchNorm1d weight / bias gradients (must be NULL in NORMALIZE mode).  1 launch (NORMALIZE) or 2. */
+int ffc_tail_backward(const ffc_tail_args* a, const float* dp_dev, int64_t dp_stride, float* dx_dev, float* dgamma_dev,
+                      float* dbeta_dev, void* stream);
+
 /* fp32 -> bf16 mirror of n contiguous elements (queue initialisation / checkpoint load). */
 int ffc_cast_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n, void* stream);
 

@@ -31,6 +31,13 @@ class HeadStats(C.Structure):
     _fields_ = [('lsum', c_void_p), ('osum', c_void_p), ('tgt', c_void_p), ('topv', c_void_p), ('topi', c_void_p)]
 
 
+class TailArgs(C.Structure):
+    _fields_ = [('x', c_void_p), ('p', c_void_p), ('p_stride', c_int64), ('inv_norm', c_void_p), ('n_rows', c_int32), ('feat_dim', c_int32),
+                ('mode', c_int32), ('eps', c_float), ('momentum', c_float), ('gamma', c_void_p), ('beta', c_void_p),
+                ('running_mean', c_void_p), ('running_var', c_void_p), ('save_mean', c_void_p), ('save_invstd', c_void_p),
+                ('workspace', c_void_p), ('workspace_bytes', c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/ffc_b200.h declares
 PROTOTYPES = {
     'ffc_last_error': (C.c_char_p, []),
@@ -62,6 +69,9 @@ PROTOTYPES = {
     'ffc_route_keys': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ffc_ema_chunk_elems': (c_int, []),
     'ffc_ema_update': (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),
+    'ffc_tail_workspace_bytes': (c_int, [c_int, c_int, C.POINTER(c_int64)]),
+    'ffc_tail_forward': (c_int, [C.POINTER(TailArgs), c_void_p]),
+    'ffc_tail_backward': (c_int, [C.POINTER(TailArgs), c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ffc_head_set_timing': (c_int, [c_void_p, c_int]),
     'ffc_head_get_timing': (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64)]),
     'ffc_head_stats_bytes': (c_int, [C.POINTER(HeadConfig), c_int, C.POINTER(c_int64)]),
