@@ -80,20 +80,29 @@ __global__ void __launch_bounds__(32 * TAIL_COL_WARPS) tail_col_stats_kernel(con
   __syncthreads();
   if (ticket != (unsigned int)(n_slabs - 1)) return;
   __threadfence();
+  // last CTA of the column group: warp y takes slabs y, y + 8, ... (loads batched), the 8 warp sums are added in warp order
+  __shared__ double redd[TAIL_COL_WARPS][33];
+  double ms = 0.0;
+  if (ok) {
+#pragma unroll 8
+    for (int j = threadIdx.y; j < n_slabs; j += TAIL_COL_WARPS) {
+      const int nj = min(B, (j + 1) * slab_rows) - j * slab_rows;
+      ms += (double)nj * (double)__ldcg(&partial[((int64_t)j * 2 + 0) * D + c]);
+    }
+  }
+  const double mean = tail_col_reduce(ms, redd) / (double)B;
+  double m2s = 0.0;
+  if (ok) {
+#pragma unroll 8
+    for (int j = threadIdx.y; j < n_slabs; j += TAIL_COL_WARPS) {
+      const int nj = min(B, (j + 1) * slab_rows) - j * slab_rows;
+      const double d = (double)__ldcg(&partial[((int64_t)j * 2 + 0) * D + c]) - mean;
+      m2s += (double)__ldcg(&partial[((int64_t)j * 2 + 1) * D + c]) + (double)nj * d * d;
+    }
+  }
+  const double m2 = tail_col_reduce(m2s, redd);
   if (threadIdx.y == 0) {
     if (ok) {
-      double mean = 0.0;
-      for (int j = 0; j < n_slabs; ++j) {
-        const int nj = min(B, (j + 1) * slab_rows) - j * slab_rows;
-        mean += (double)nj * (double)__ldcg(&partial[((int64_t)j * 2 + 0) * D + c]);
-      }
-      mean /= (double)B;
-      double m2 = 0.0;
-      for (int j = 0; j < n_slabs; ++j) {
-        const int nj = min(B, (j + 1) * slab_rows) - j * slab_rows;
-        const double d = (double)__ldcg(&partial[((int64_t)j * 2 + 0) * D + c]) - mean;
-        m2 += (double)__ldcg(&partial[((int64_t)j * 2 + 1) * D + c]) + (double)nj * d * d;
-      }
       const float var_b = (float)(m2 / (double)B);                                  // biased: what normalises the batch
       save_mean[c] = (float)mean;
       save_invstd[c] = 1.0f / sqrtf(var_b + eps);
@@ -295,11 +304,13 @@ __global__ void __launch_bounds__(32 * TAIL_COL_WARPS) tail_cols_dx_kernel(const
   const int c = blockIdx.x * 32 + threadIdx.x;
   const bool ok = c < D;
   double s1 = 0.0, s2 = 0.0;
-  if (ok)
+  if (ok) {
+#pragma unroll 8
     for (int j = threadIdx.y; j < n_partial; j += TAIL_COL_WARPS) {
       s1 += (double)partial[((int64_t)j * 2 + 0) * D + c];
       s2 += (double)partial[((int64_t)j * 2 + 1) * D + c];
     }
+  }
   s1 = tail_col_reduce(s1, red);
   s2 = tail_col_reduce(s2, red);
   if (!ok) return;
@@ -323,7 +334,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // slab geometry (shared by ffc_tail_workspace_bytes and the launches)
 struct TailGeom {
   int fwd_slab_rows, fwd_slabs;      // column statistics: <= 64 slabs of >= 32 rows
-  int bwd_rows_per_cta, bwd_ctas;    // backward row kernel: 8 rows per CTA up to 2048 rows, <= 256 CTAs beyond
+  int bwd_rows_per_cta, bwd_ctas;    // backward row kernel: 16 rows per CTA up to 2048 rows, <= 128 CTAs beyond
   int64_t counter_bytes, partial_floats;
 };
 static TailGeom tail_geom(int B, int D) {
@@ -331,7 +342,7 @@ static TailGeom tail_geom(int B, int D) {
   const int want = std::min((B + 31) / 32, 64);
   g.fwd_slab_rows = (B + want - 1) / want;
   g.fwd_slabs = (B + g.fwd_slab_rows - 1) / g.fwd_slab_rows;
-  g.bwd_rows_per_cta = B <= 2048 ? TAIL_COL_WARPS : ((B + 255) / 256 + TAIL_COL_WARPS - 1) / TAIL_COL_WARPS * TAIL_COL_WARPS;
+  g.bwd_rows_per_cta = B <= 2048 ? 2 * TAIL_COL_WARPS : ((B + 127) / 128 + TAIL_COL_WARPS - 1) / TAIL_COL_WARPS * TAIL_COL_WARPS;
   g.bwd_ctas = (B + g.bwd_rows_per_cta - 1) / g.bwd_rows_per_cta;
   g.counter_bytes = ((int64_t)((D + 31) / 32) * 4 + 255) / 256 * 256;
   g.partial_floats = (int64_t)std::max(g.fwd_slabs, g.bwd_ctas) * 2 * D;

@@ -20,6 +20,7 @@ from torch.nn import Module
 from . import _capi
 from ._capi import HeadConfig, HeadPass, HeadStats, check, ptr
 from .lru import LRU
+from .tail import l2_normalize
 
 
 def hard_neg_k(queue_size: int) -> int:
@@ -36,7 +37,7 @@ class NormalizeNet(Module):
         self.dummy = torch.nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
-        return F.normalize(x + 0.0 * self.dummy)
+        return l2_normalize(x + 0.0 * self.dummy)       # csrc/tail.cu: the head normalises the embeddings it is fed
 
 
 def _default_create_net(net_type, **kwargs):

@@ -77,7 +77,9 @@ class _TailFn(torch.autograd.Function):
         ctx.save_for_backward(x32)
         # everything else `args` points into.  `out` is read by backward through its address: it may live in a staging buffer
         # whose other columns are legitimately written in between (torch's version counter is per storage)
-        ctx.args, ctx.keep = args, (out, inv_norm, stats, w32, b32, running_mean, running_var)
+        # (a detached alias, not `out` itself: `out` is this node's output, holding it here would be a reference cycle that only
+        # the cyclic GC frees)
+        ctx.args, ctx.keep = args, (out.detach(), inv_norm, stats, w32, b32, running_mean, running_var)
         ctx.in_dtype = x.dtype
         ctx.grads = (weight is not None and weight.requires_grad, bias is not None and bias.requires_grad)
         ctx.param_dtypes = (None if weight is None else weight.dtype, None if bias is None else bias.dtype)
