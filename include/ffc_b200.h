@@ -243,6 +243,14 @@ typedef struct ffc_head_stats {
 
 int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream);
 
+/* ffc_head_sweep in two steps, for the SV loss on a sharded queue (ffc.py:116-138): SV's hard-example threshold is the row's
+ * target cosine minus the margin (ffc.py:121-122), and on R > 1 ranks only the owner of the target column can compute it.
+ * ffc_head_prep writes out->tgt (target cosines, owner flag; zero where the target is not local); the caller sums tgt over the
+ * ranks (all-reduce); ffc_head_sweep_prepared re-derives the thresholds from the summed tgt and runs the sweeps.  For AM / Arc
+ * the pair is equivalent to ffc_head_sweep (the sweeps do not read tgt).  `in` / `out` must be the same in both calls. */
+int ffc_head_prep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream);
+int ffc_head_sweep_prepared(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream);
+
 /* Finalize: loss_out[0] = this pass's loss (both add_margin terms) -- identical on every rank when
  * stats were reduced; dp_out [n_rows, D] fp32 = this rank's contribution to dLoss/dp (the whole
  * gradient on one GPU).  n_ranks_topk: number of gathered top-k candidate sets in stats->topv/topi

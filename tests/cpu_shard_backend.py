@@ -87,9 +87,38 @@ class CpuShardBackend:
         tpos = torch.tensor([pos.get(int(t), -1) for t in tcol.tolist()], dtype=torch.long)
         return tcol, tpos
 
-    def sweep(self, p_all, label, st, slot):
+    SV_T = 1.2        # ffc.py:47 mask_svfc
+
+    def _fixed_max(self):
+        """csrc/head.cu fixed_max_of: the largest scaled logit any column can reach (SV lifts hard examples to T*cos + T - 1)"""
+        return self.scale * (2 * self.SV_T - 1) if self.loss_type == 'SV' else self.scale
+
+    def prep(self, p_all, label, st, slot):
+        """target cosines under queue[0] / W2 and the owner flag (ffc_head_prep)"""
         p = p_all.double()
-        n, k, s, M = p.shape[0], self.k, self.scale, self.scale
+        n = p.shape[0]
+        tcol, tpos = self._row_info(label)
+        W0, W1 = self.queue[0], self.queue[1]
+        ar = torch.arange(n)
+        has_t = tcol >= 0
+        t0 = torch.zeros(n, dtype=torch.float64)
+        t1 = torch.zeros(n, dtype=torch.float64)
+        rows = ar[has_t]
+        t0[rows] = (p[rows] * W0[tcol[rows]]).sum(1)
+        wt = torch.where((tpos[rows] >= 0).unsqueeze(1), W1[tcol[rows]], W0[tcol[rows]])
+        t1[rows] = (p[rows] * wt).sum(1)
+        red = st['red']
+        red[4], red[5], red[6], red[7] = t0, t1, has_t.double(), torch.zeros(n, dtype=torch.float64)
+
+    def sweep(self, p_all, label, st, slot):
+        self.prep(p_all, label, st, slot)
+        self.sweep_prepared(p_all, label, st, slot)
+
+    def sweep_prepared(self, p_all, label, st, slot):
+        """the sweeps proper; SV reads the (all-reduced) target cosines of st['red'][4:6] for its thresholds (ffc_head_sweep_prepared)"""
+        p = p_all.double()
+        n, k, s, M = p.shape[0], self.k, self.scale, self._fixed_max()
+        sv, T = self.loss_type == 'SV', self.SV_T
         tcol, tpos = self._row_info(label)
         out = label < 0
         W0, W1 = self.queue[0], self.queue[1]
@@ -101,9 +130,25 @@ class CpuShardBackend:
         ar = torch.arange(n)
         has_t = tcol >= 0
         excl[ar[has_t], tcol[has_t]] = True
-        pt = torch.exp(s * cos - M).masked_fill(excl, 0.0)
-        red[0] = red[1] = pt.sum(1)
-        osum[0] = osum[1] = pt @ W0
+        if sv:   # ffc.py:121-125: columns with cos > gt - margin become T*cos + T - 1 (gradient factor T); thresholds per loss
+            inf = torch.full((n,), math.inf, dtype=torch.float64)
+            thr = [torch.where(red[6] > 0, red[4 + l] - self.margin, inf) for l in range(2)]
+
+            def terms(c, l):
+                hard = c > thr[l].unsqueeze(1)
+                z = torch.where(hard, T * c + T - 1.0, c)
+                return torch.exp(s * z - M), torch.where(hard, torch.full_like(c, T), torch.ones_like(c))
+            for l in range(2):
+                pt, coef = terms(cos, l)
+                pt = pt.masked_fill(excl, 0.0)
+                red[l] = pt.sum(1)
+                osum[l] = (pt * coef) @ W0
+        else:
+            def terms(c, l):
+                return torch.exp(s * c - M), torch.ones_like(c)
+            pt = torch.exp(s * cos - M).masked_fill(excl, 0.0)
+            red[0] = red[1] = pt.sum(1)
+            osum[0] = osum[1] = pt @ W0
         st['topv'][slot].fill_(-math.inf)
         st['topi'][slot].fill_(-1)
 
@@ -127,20 +172,14 @@ class CpuShardBackend:
             ex = torch.zeros(n, len(self.ones), dtype=torch.bool)
             has_p = tpos >= 0
             ex[ar[has_p], tpos[has_p]] = True
-            ps = torch.exp(s * cs - M).masked_fill(ex, 0.0)
+            ps, coef = terms(cs, l)
+            ps = ps.masked_fill(ex, 0.0)
             red[2 + l] = ps.sum(1)
-            osum[2 + l] = ps @ Ws
+            osum[2 + l] = (ps * coef) @ Ws
             put_topk(cs, self.off + ones, torch.zeros_like(ex), 1 + l)
-        t0 = torch.zeros(n, dtype=torch.float64)
-        t1 = torch.zeros(n, dtype=torch.float64)
-        rows = ar[has_t]
-        t0[rows] = (p[rows] * W0[tcol[rows]]).sum(1)
-        wt = torch.where((tpos[rows] >= 0).unsqueeze(1), W1[tcol[rows]], W0[tcol[rows]])
-        t1[rows] = (p[rows] * wt).sum(1)
-        red[4], red[5], red[6], red[7] = t0, t1, has_t.double(), torch.zeros(n, dtype=torch.float64)
 
     def finalize(self, p_all, label, st, n_ranks):
-        n, D, k, s, M, m = p_all.shape[0], self.D, self.k, self.scale, self.scale, self.margin
+        n, D, k, s, M, m = p_all.shape[0], self.D, self.k, self.scale, self._fixed_max(), self.margin
         tcol, tpos = self._row_info(label)
         out = label < 0
         n_pos, n_out = int((~out).sum()), int(out.sum())
@@ -152,16 +191,19 @@ class CpuShardBackend:
             if not out[i]:
                 for l in range(2):
                     ct = float(red[4 + l, i])
+                    cs = l if self.loss_type == 'SV' else 0       # SV: each loss has its own common statistics (own threshold)
                     if self.loss_type == 'AM':
                         ft, dft = ct - m, 1.0
+                    elif self.loss_type == 'SV':
+                        ft, dft = (ct - m if ct > m else ct), 1.0  # ffc.py:123 final_gt
                     else:
                         sn = math.sqrt(1.0 - ct * ct)
                         ft, dft = ct * math.cos(m) - sn * math.sin(m), math.cos(m) + ct * math.sin(m) / sn
                     zt = s * ft
                     et = math.exp(zt - M)
-                    L = float(red[l, i] + red[2 + l, i]) + et
+                    L = float(red[cs, i] + red[2 + l, i]) + et
                     loss += (math.log(L) + M - zt) / n_pos
-                    dp[i] += (s / L / n_pos) * (osum[l, i] + osum[2 + l, i])
+                    dp[i] += (s / L / n_pos) * (osum[cs, i] + osum[2 + l, i])
                     if tcol[i] >= 0:
                         row = 1 if (l == 1 and tpos[i] >= 0) else 0
                         dp[i] += (s * (et / L - 1.0) * dft / n_pos) * W[row, tcol[i]]

@@ -102,7 +102,7 @@ def _worker(rank, world, port, loss_type, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('loss_type', ['AM', 'Arc'])
+@pytest.mark.parametrize('loss_type', ['AM', 'Arc', 'SV'])
 def test_sharded_head_world2_gloo(loss_type):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

@@ -34,6 +34,7 @@ struct ffc_head {
   float* thr;                  // [2][max_rows]
   int32_t* counts;             // [2][2] n_pos, n_out, double-buffered by pass parity
   int pass_parity;
+  int prepared_rows;           // rows of the last ffc_head_prep not yet swept (ffc_head_prep / ffc_head_sweep_prepared pairing), else <= 0
   ffc::ReduceJobs* jobs;        // partial-result descriptors of the last merged sweep launch (one-GPU fast path)
   int jobs_pending;            // 1: the last sweep left its partials unreduced for head_finalize_fused_kernel
   float* row_loss;             // [max_rows]
@@ -1067,7 +1068,18 @@ static int run_merged_sweeps(ffc_head* h, SweepArgs a, const ffc_head_pass* in, 
   return FFC_OK;
 }
 
-static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, bool defer_reduce, void* stream) {
+// SV on a sharded queue: the hard-example threshold (ffc.py:122, gt - margin) of a row whose target column lives on another rank.
+// tgt holds the all-reduced target cosines ([0], [1]) and owner count ([2]) written by the ranks' prep launches.
+__global__ void __launch_bounds__(128) head_thr_from_tgt_kernel(const float* __restrict__ tgt, int n, float margin, float* __restrict__ thr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool has = tgt[2 * n + i] > 0.f;
+  thr[i] = has ? tgt[i] - margin : INFINITY;
+  thr[n + i] = has ? tgt[n + i] - margin : INFINITY;
+}
+
+// phase: 1 = prep only, 2 = sweeps only (prep was run by ffc_head_prep; SV thresholds are re-derived from out->tgt), 3 = both
+static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, bool defer_reduce, void* stream, int phase = 3) {
   FFC_REQUIRE(h && in && out, "ffc_head_sweep: NULL argument");
   h->jobs_pending = 0;
   const ffc_head_config& c = h->cfg;
@@ -1082,7 +1094,7 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
   const __nv_bfloat16* qh = (const __nv_bfloat16*)in->queue_bf16;
 
   const bool sv = c.loss_type == FFC_LOSS_SV;
-  {
+  if (phase & 1) {
     // counts double-buffered by pass parity (see head_prep_fused_kernel)
     h->pass_parity ^= 1;
     int32_t* cur = h->counts + 2 * h->pass_parity;
@@ -1097,7 +1109,17 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
                                                          in->n_ones, c.max_rows, h->side_f32, nullptr, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
                                                          out->tgt, sv ? h->thr : nullptr);
     FFC_LAUNCH_CHECK();
+    h->prepared_rows = n;
   }
+  if (phase == 1) return FFC_OK;
+  if (phase == 2) {
+    FFC_REQUIRE(h->prepared_rows == n && n > 0, "ffc_head_sweep_prepared: ffc_head_prep was not run for these %d rows", n);
+    if (sv) {
+      head_thr_from_tgt_kernel<<<(n + 127) / 128, 128, 0, s>>>(out->tgt, n, c.margin, h->thr);
+      FFC_LAUNCH_CHECK();
+    }
+  }
+  h->prepared_rows = 0;
 
   SweepArgs a;
   memset(&a, 0, sizeof(a));
@@ -1142,6 +1164,14 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
 
 extern "C" int ffc_head_sweep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
   return head_sweep_impl(h, in, out, false, stream);
+}
+
+extern "C" int ffc_head_prep(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
+  return head_sweep_impl(h, in, out, false, stream, 1);
+}
+
+extern "C" int ffc_head_sweep_prepared(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, void* stream) {
+  return head_sweep_impl(h, in, out, false, stream, 2);
 }
 
 static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* stats, int n_ranks_topk, float* loss_out, float* dp_out,

@@ -60,6 +60,8 @@ PROTOTYPES = {
     'ffc_head_create': (c_int, [C.POINTER(HeadConfig), C.POINTER(c_void_p)]),
     'ffc_head_destroy': (c_int, [c_void_p]),
     'ffc_head_sweep': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_void_p]),
+    'ffc_head_prep': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_void_p]),
+    'ffc_head_sweep_prepared': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_void_p]),
     'ffc_head_finalize': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_int, c_void_p, c_void_p, c_void_p]),
     'ffc_head_pass_single': (c_int, [c_void_p, C.POINTER(HeadPass), C.POINTER(HeadStats), c_void_p, c_void_p, c_void_p]),
     'ffc_head_record_words': (c_int, [C.POINTER(HeadConfig), c_int, C.POINTER(c_int64)]),

@@ -10,6 +10,7 @@ One head pass (embeddings in) per rank:
   own gallery keys  -> device LRU assign + enqueue scatter into the local shard      (ffc.py:162-182 / 214-241)
   probe labels      -> local view, global slot = r*Q/R + local, all-reduce MAX       (ffc.py:189-194)
   sweep of the local shard for ALL R*B rows        (same tcgen05 kernel as on one GPU)
+  [SV only: the target cosines are all-reduced BEFORE the sweep -- its hard-example threshold is gt - margin, ffc.py:121-122]
   all-reduce SUM of the per-row softmax denominators / target cosines, all-gather of the top-k candidates
   finalize -> loss (identical on every rank) and this rank's partial dLoss/dp for all rows
   reduce-scatter SUM -> dLoss/dp of the rank's own B rows
@@ -163,6 +164,15 @@ class CudaShardBackend:
         hp, hs = self._structs(p_all, label, st, rank_slot)
         check(self.lib.ffc_head_sweep(self._h, C.byref(hp), C.byref(hs), self._s()))
 
+    def prep(self, p_all, label, st, rank_slot):
+        """first half of :meth:`sweep`: target cosines / owner flags into st['red'][4:8] (SV: summed over the ranks before the sweep)"""
+        hp, hs = self._structs(p_all, label, st, rank_slot)
+        check(self.lib.ffc_head_prep(self._h, C.byref(hp), C.byref(hs), self._s()))
+
+    def sweep_prepared(self, p_all, label, st, rank_slot):
+        hp, hs = self._structs(p_all, label, st, rank_slot)
+        check(self.lib.ffc_head_sweep_prepared(self._h, C.byref(hp), C.byref(hs), self._s()))
+
     def finalize(self, p_all, label, st, n_ranks):
         hp, hs = self._structs(p_all, label, st, 0)
         dp = torch.empty(p_all.shape[0], self.D, dtype=torch.float32, device=self.dev)
@@ -202,7 +212,8 @@ class ShardedFFCHead:
     def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024, device=None,
                  group=None, backend_factory=None):
         assert dist.is_initialized(), 'torch.distributed must be initialised (one process per GPU)'
-        assert loss_type in ('AM', 'Arc'), 'the sharded head supports AM / Arc (SV needs the target cosine before the sweep)'
+        assert loss_type in ('AM', 'Arc', 'SV')
+        self.loss_type = loss_type
         self.group = group
         self.R = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -381,9 +392,18 @@ class ShardedFFCHead:
         st = self._stats.get(n)
         if st is None:
             st = self._stats[n] = be.new_stats(n, R)
-        be.sweep(p_all, label, st, self.rank)
-        self._mark('sweep')
-        dist.all_reduce(st['red'], group=self.group)
+        if self.loss_type == 'SV':
+            # ffc.py:121-122: the hard-example threshold of a row is its target cosine - margin, known only to the rank that owns the
+            # target column: sum the target cosines over the ranks first (owner's value + zeros), then sweep
+            be.prep(p_all, label, st, self.rank)
+            dist.all_reduce(st['red'][4:], group=self.group)
+            be.sweep_prepared(p_all, label, st, self.rank)
+            self._mark('sweep')
+            dist.all_reduce(st['red'][:4], group=self.group)
+        else:
+            be.sweep(p_all, label, st, self.rank)
+            self._mark('sweep')
+            dist.all_reduce(st['red'], group=self.group)
         if R > 1 and st['topv'].dtype != torch.float32:     # CPU stand-in backend (fp64 values): two plain gathers
             tv, ti = st['topv'][self.rank].clone(), st['topi'][self.rank].clone()
             dist.all_gather_into_tensor(st['topv'].view(R * 3, n, -1), tv, group=self.group)
