@@ -19,7 +19,9 @@ def main():
     dist.init_process_group('nccl', device_id=dev)
     for precision, tol, D, Q, B, n_ids, loss_type, margin in (('bf16', 1e-2, 128, 1024, 96, 1500, 'Arc', 0.5),
                                                                ('fp32', 1e-5, 64, 512, 40, 700, 'AM', 0.4),
-                                                               ('bf16', 1e-2, 512, 4096, 128, 4096, 'AM', 0.4)):
+                                                               ('bf16', 1e-2, 512, 4096, 128, 4096, 'AM', 0.4),
+                                                               ('bf16', 1e-2, 128, 1024, 96, 1500, 'SV', 0.4),
+                                                               ('fp32', 1e-5, 64, 512, 40, 700, 'SV', 0.4)):
         torch.manual_seed(0)
         q0 = F.normalize(torch.rand(2, Q, D), dim=2)
         head = ShardedFFCHead(D, Q, 32.0, loss_type, margin, precision=precision, max_batch=B, device=dev)
@@ -28,7 +30,7 @@ def main():
         oracle = ShardedOracle(world, D, Q, 32.0, loss_type, margin, queue=q0, dtype=torch.float64)
         gen = torch.Generator().manual_seed(5)
         cen = F.normalize(torch.randn(n_ids, D, generator=gen))
-        for s in range(3):
+        for s in range(6):
             n = world * B
             xl = torch.randint(0, n_ids, (n,), generator=gen)
             yl = torch.cat([xl[:n // 2], torch.randint(0, n_ids, (n - n // 2,), generator=gen)])
@@ -40,6 +42,23 @@ def main():
             if s == 2:      # the overlapped two-pass entry used by bench.py (commit bookkeeping under the rollback sweep)
                 loss, gx, gy = head.forward_pair(xs.detach(), ys.detach(), xl[sl], yl[sl])
                 xs.grad, ys.grad = gx, gy
+            elif s == 3:    # labels handed over early (CPU tensors): the rollback bookkeeping runs on the bookkeeping stream
+                head.prefetch(xl[sl], yl[sl])
+                assert head._pre is not None
+                loss, gx, gy = head.forward_pair(xs.detach(), ys.detach())
+                xs.grad, ys.grad = gx, gy
+            elif s == 4:    # a stale prefetch (other labels) is discarded without a trace, then the same objects are accepted
+                mine = (xl[sl], yl[sl])
+                head.prefetch(yl[sl].clone(), xl[sl].clone())
+                head.prefetch(*mine)
+                pre = head._pre
+                loss, gx, gy = head.forward_pair(xs.detach(), ys.detach(), *mine)
+                assert pre is not None and head._pre is None and head._last['label'] is pre['ctx']['label']
+                xs.grad, ys.grad = gx, gy
+            elif s == 5:    # stale prefetch followed by the autograd entry
+                head.prefetch(yl[sl].clone(), xl[sl].clone())
+                loss = head.forward(xs, ys, xl[sl], yl[sl])
+                loss.backward()
             else:
                 loss = head.forward(xs, ys, xl[sl], yl[sl])
                 loss.backward()

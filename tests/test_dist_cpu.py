@@ -102,6 +102,63 @@ def _worker(rank, world, port, loss_type, ret):
         dist.destroy_process_group()
 
 
+def _worker_prefetch(rank, world, port, ret):
+    """prefetch(labels) + forward_pair(x, y) == forward_pair(x, y, labels), step for step (loss, gradients, LRU, queue), including a
+    prefetch that is discarded because other labels arrive"""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from cpu_shard_backend import CpuShardBackend
+        from ffc_b200.dist import ShardedFFCHead
+        D, Q, B, n_ids, steps = 16, 64, 12, 90, 5
+        q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64), dim=2)
+        mk = lambda: ShardedFFCHead(D, Q, 32.0, 'Arc', 0.5, max_batch=B,
+                                    backend_factory=lambda ql, off, n: CpuShardBackend(D, ql, Q, off, n, 32.0, 'Arc', 0.5, hard_neg_k(Q),
+                                                                                       queue=q0[:, off:off + ql]))
+        plain, pre = mk(), mk()
+        gen = torch.Generator().manual_seed(6)
+        cen = F.normalize(torch.randn(n_ids, D, generator=gen, dtype=torch.float64))
+        batches = []
+        for s in range(steps):
+            xl = torch.randint(0, n_ids, (B,), generator=gen)
+            yl = torch.cat([xl[:B // 2], torch.randint(0, n_ids, (B - B // 2,), generator=gen)])
+            g2 = torch.Generator().manual_seed(100 * s + rank)
+            x = F.normalize(cen[xl] + 0.4 * torch.randn(B, D, generator=g2, dtype=torch.float64))
+            y = F.normalize(cen[yl] + 0.4 * torch.randn(B, D, generator=g2, dtype=torch.float64))
+            batches.append((x, y, xl + rank, yl + rank))       # different labels per rank
+        pre.prefetch(batches[0][2], batches[0][3])
+        for s, (x, y, xl, yl) in enumerate(batches):
+            a = plain.forward_pair(x, y, xl, yl)
+            if s == 2:      # stale prefetch: labels of another batch were handed over, then this batch arrives with its own
+                pre.prefetch(batches[4][2], batches[4][3])
+                b = pre.forward_pair(x, y, xl, yl)
+            elif s == 3:    # prefetched labels, passed again as the same objects
+                b = pre.forward_pair(x, y, xl, yl)
+            else:
+                b = pre.forward_pair(x, y)
+            if s + 1 < steps and s + 1 != 2:
+                pre.prefetch(batches[s + 1][2], batches[s + 1][3])
+            for u, v in zip(a, b):
+                assert torch.equal(u, v), s
+            assert plain.backend.lru.state_dict() == pre.backend.lru.state_dict()
+            assert plain.backend.qpos == pre.backend.qpos and torch.equal(plain.backend.queue, pre.backend.queue)
+        ret[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_head_label_prefetch_world2_gloo():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_prefetch, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: 'ok', 1: 'ok'}
+
+
 @pytest.mark.parametrize('loss_type', ['AM', 'Arc', 'SV'])
 def test_sharded_head_world2_gloo(loss_type):
     import sys

@@ -234,15 +234,25 @@ class ShardedFFCHead:
         import os
         self._timing = [] if (os.environ.get('FFC_DIST_TIMING') and self._nccl) else None
         self._side = torch.cuda.Stream(device=self.dev) if (self._nccl and not os.environ.get('FFC_DIST_NO_OVERLAP')) else None
+        self._pre = None            # labels + rollback-pass bookkeeping of the next forward_pair (see prefetch)
+        # prefetch's collectives get their own communicator: torch's NCCL backend runs all collectives of one process group on one
+        # internal stream in issue order, so on the main group they would queue behind the current step's record all-gather /
+        # reduce-scatter, i.e. behind the very sweeps they are meant to run under
+        self._side_group = None
+        if self._side is not None:
+            ranks = dist.get_process_group_ranks(group) if group is not None else None
+            self._side_group = dist.new_group(ranks=ranks, backend='nccl')
+        self._rb_done = None        # event: the last pass that used bookkeeping set 0 has finished with it
+        self._lru_main_ev = None    # event: the last bookkeeping enqueued on the caller's stream (the LRU state prefetch builds on)
 
     # -- helpers ----------------------------------------------------------------------------------
     def shard_of(self, keys):
         """Owner rank of each identity: floor-mod (exact and balanced for dense class indices)."""
         return torch.remainder(keys, self.R)
 
-    def _all_gather(self, t):
+    def _all_gather(self, t, group=None):
         out = torch.empty((self.R * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group if group is not None else self.group)
         return out
 
     def _reduce_scatter(self, t):
@@ -286,39 +296,134 @@ class ShardedFFCHead:
         l_all = self._all_gather(torch.as_tensor(label).to(device=dev, dtype=torch.int64))
         return e_all, l_all
 
-    def gather_pair(self, x, y, x_label, y_label):
+    def gather_pair(self, x, y, x_label=None, y_label=None):
         """Both sides of the batch in ONE all-gather (NCCL): each rank contributes [x | y | x_label | y_label] as one packed
-        buffer of 4-byte words.  Returns (x_all, xl_all, y_all, yl_all) in global batch order (rank-major)."""
+        buffer of 4-byte words.  Returns (x_all, xl_all, y_all, yl_all) in global batch order (rank-major); without labels
+        (they were exchanged by :meth:`prefetch`) the buffer is [x | y] and the label entries are None."""
+        with_labels = x_label is not None
         if not self._nccl:
-            return self.gather(x, x_label) + self.gather(y, y_label)
+            if with_labels:
+                return self.gather(x, x_label) + self.gather(y, y_label)
+            fdt = getattr(self.backend, 'dtype', torch.float32)
+            return (self._all_gather(x.detach().to(device=self.dev, dtype=fdt)), None, self._all_gather(y.detach().to(device=self.dev, dtype=fdt)), None)
         dev, B, D, R = self.dev, self.B, self.D, self.R
         assert x.shape == (B, D) and y.shape == (B, D), f'every rank must feed max_batch={B} rows of {D} features'
         ne = B * D
-        own = torch.empty(2 * ne + 4 * B, dtype=torch.float32, device=dev)
+        own = torch.empty(2 * ne + (4 * B if with_labels else 0), dtype=torch.float32, device=dev)
         own[:ne].view(B, D).copy_(x.detach())
         own[ne:2 * ne].view(B, D).copy_(y.detach())
-        lab = own[2 * ne:].view(torch.int64)
-        lab[:B].copy_(torch.as_tensor(x_label).reshape(B), non_blocking=True)
-        lab[B:].copy_(torch.as_tensor(y_label).reshape(B), non_blocking=True)
+        if with_labels:
+            lab = own[2 * ne:].view(torch.int64)
+            lab[:B].copy_(torch.as_tensor(x_label).reshape(B), non_blocking=True)
+            lab[B:].copy_(torch.as_tensor(y_label).reshape(B), non_blocking=True)
         buf = torch.empty(R, own.numel(), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(buf, own, group=self.group)
+        x_all, y_all = buf[:, :ne].reshape(R * B, D), buf[:, ne:2 * ne].reshape(R * B, D)
+        if not with_labels:
+            return x_all, None, y_all, None
         labs = buf[:, 2 * ne:].view(torch.int64)                      # [R, 2B]
-        return (buf[:, :ne].reshape(R * B, D), labs[:, :B].reshape(R * B), buf[:, ne:2 * ne].reshape(R * B, D), labs[:, B:].reshape(R * B))
+        return x_all, labs[:, :B].reshape(R * B), y_all, labs[:, B:].reshape(R * B)
+
+    # -- label prefetch (SURVEY 8(f) rank 4: the labels of a step are known long before its embeddings) --------------------------
+    def prefetch(self, x_label, y_label):
+        """Hand over the labels of the NEXT :meth:`forward_pair` now.  They are all-gathered and the rollback pass's bookkeeping
+        (route, LRU try_get + undo, probe labels: ffc.py:214-235, 242-246, 256-259) is enqueued on the bookkeeping stream, where
+        it runs underneath the sweeps already queued on the caller's stream (it only needs the LRU state the previous commit
+        pass left, and bookkeeping set 0, which the previous rollback pass has released).  The next forward_pair must be given
+        these same label objects (or none); any other call discards the prefetched work, which leaves no trace (a rollback
+        pass's bookkeeping undoes itself).  Pass CPU tensors (the reference's contract, main.py:59-60): CUDA labels make the
+        bookkeeping stream wait for the caller's stream, i.e. no overlap."""
+        self._discard_prefetch()
+        B = self.B
+        if self._side is None:
+            xl_all, yl_all = self._gather_labels(x_label, y_label)
+            ctx = self._bookkeep(xl_all, yl_all, False, 0)
+            self._pre = dict(xl=xl_all, yl=yl_all, ctx=ctx, ev=None, src=(x_label, y_label))
+            return
+        main = torch.cuda.current_stream(self.dev)
+        on_dev = any(torch.is_tensor(t) and t.is_cuda for t in (x_label, y_label))
+        with torch.cuda.stream(self._side):
+            if on_dev:
+                ev_in = torch.cuda.Event()
+                ev_in.record(main)
+                self._side.wait_event(ev_in)
+            for e in (self._rb_done, self._lru_main_ev):
+                if e is not None:
+                    self._side.wait_event(e)
+            timing, self._timing = self._timing, None
+            xl_all, yl_all = self._gather_labels(x_label, y_label, self._side_group)
+            ctx = self._bookkeep(xl_all, yl_all, False, 0, group=self._side_group)
+            self._timing = timing
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._pre = dict(xl=xl_all, yl=yl_all, ctx=ctx, ev=ev, src=(x_label, y_label))
+
+    def _gather_labels(self, x_label, y_label, group=None):
+        B, R = self.B, self.R
+        own = torch.empty(2 * B, dtype=torch.int64, device=self.dev)
+        own[:B].copy_(torch.as_tensor(x_label).reshape(B), non_blocking=True)
+        own[B:].copy_(torch.as_tensor(y_label).reshape(B), non_blocking=True)
+        labs = self._all_gather(own, group).view(R, 2 * B)
+        return labs[:, :B].reshape(R * B), labs[:, B:].reshape(R * B)
+
+    def _discard_prefetch(self):
+        pre, self._pre = self._pre, None
+        if pre is None:
+            return
+        # the LRU / queue positions were restored by the bookkeeping itself; only set 0's `ones` mask has to be cleared
+        be = self.backend
+        if self._side is not None:
+            with torch.cuda.stream(self._side):
+                if hasattr(be, 'use_set'):
+                    be.use_set(0)
+                be.end_pass()
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            torch.cuda.current_stream(self.dev).wait_event(ev)
+        else:
+            if hasattr(be, 'use_set'):
+                be.use_set(0)
+            be.end_pass()
+
+    def _take_prefetch(self, x_label, y_label):
+        pre = self._pre
+        if pre is None:
+            return None
+        if (x_label is None and y_label is None) or (x_label is pre['src'][0] and y_label is pre['src'][1]):
+            self._pre = None
+            return pre
+        self._discard_prefetch()
+        return None
 
     def head_pass(self, p, g, probe_label, gallery_label, commit):
+        self._discard_prefetch()
         self._mark('start')
         p_all, pl_all = self.gather(p, probe_label)
         g_all, gl_all = self.gather(g, gallery_label)
         self._mark('all_gather')
         return self.head_pass_gathered(p_all, g_all, pl_all, gl_all, commit)
 
-    def forward_pair(self, x, y, x_label, y_label):
+    def forward_pair(self, x, y, x_label=None, y_label=None):
         """ffc.py:264-267 on embeddings without autograd glue: both passes share ONE all-gather of (x, x_label) and
-        (y, y_label), since the commit pass only swaps the roles.  Returns (loss, dLoss/dx, dLoss/dy) for the rank's rows."""
+        (y, y_label), since the commit pass only swaps the roles.  Returns (loss, dLoss/dx, dLoss/dy) for the rank's rows.
+        After :meth:`prefetch` the labels (and the rollback pass's bookkeeping) are already there: only [x | y] is gathered."""
         self._mark('start')
-        x_all, xl_all, y_all, yl_all = self.gather_pair(x, y, x_label, y_label)
-        self._mark('all_gather')
-        ctx_rb = self._bookkeep(xl_all, yl_all, False, 0)
+        pre = self._take_prefetch(x_label, y_label)
+        if pre is None:
+            assert x_label is not None and y_label is not None, 'labels are required unless they were handed to prefetch()'
+            x_all, xl_all, y_all, yl_all = self.gather_pair(x, y, x_label, y_label)
+            self._mark('all_gather')
+            ctx_rb = self._bookkeep(xl_all, yl_all, False, 0)
+        else:
+            x_all, _, y_all, _ = self.gather_pair(x, y)
+            self._mark('all_gather')
+            xl_all, yl_all, ctx_rb = pre['xl'], pre['yl'], pre['ctx']
+            if pre['ev'] is not None:
+                main = torch.cuda.current_stream(self.dev)
+                main.wait_event(pre['ev'])
+                for t in list(ctx_rb.values()) + [xl_all, yl_all]:
+                    if torch.is_tensor(t):
+                        t.record_stream(main)
         if self._nccl and self._side is not None:
             # the commit pass's bookkeeping (LRU assign, probe labels) only needs the LRU state, which the rollback pass has
             # already restored: run it on a side stream underneath the rollback pass's sweep
@@ -344,7 +449,7 @@ class ShardedFFCHead:
         l1, dy = self._finish(y_all, x_all, ctx_cm, True)
         return l1 + l2, dx, dy
 
-    def _bookkeep(self, pl_all, gl_all, commit, set_idx):
+    def _bookkeep(self, pl_all, gl_all, commit, set_idx, group=None):
         """Route this rank's gallery keys, run the LRU (+ immediate undo on a rollback pass) and resolve the probe labels.
         Touches only LRU state and bookkeeping set `set_idx`; never the queue rows."""
         be = self.backend
@@ -365,8 +470,11 @@ class ShardedFFCHead:
         label = torch.where(loc >= 0, loc + self.off, loc).to(torch.int32)
         if not commit:
             be.undo_bookkeeping()
-        dist.all_reduce(label, op=dist.ReduceOp.MAX, group=self.group)
+        dist.all_reduce(label, op=dist.ReduceOp.MAX, group=group if group is not None else self.group)
         self._mark('labels')
+        if self._side is not None and torch.cuda.current_stream(self.dev) != self._side:
+            self._lru_main_ev = torch.cuda.Event()
+            self._lru_main_ev.record()
         return dict(order=order, label=label, n_mine=n_mine, set=set_idx)
 
     def _finish(self, p_all, g_all, ctx, commit):
@@ -428,6 +536,9 @@ class ShardedFFCHead:
         if not commit:
             be.restore_queue()
         be.end_pass()
+        if self._side is not None and ctx['set'] == 0:
+            self._rb_done = torch.cuda.Event()
+            self._rb_done.record()
         self._mark('restore')
         self._last = dict(label=label, n_mine=ctx['n_mine'])
         return loss, dp
