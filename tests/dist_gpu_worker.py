@@ -44,21 +44,22 @@ def main():
                 xs.grad, ys.grad = gx, gy
             elif s == 3:    # labels handed over early (CPU tensors): the rollback bookkeeping runs on the bookkeeping stream
                 head.prefetch(xl[sl], yl[sl])
-                assert head._pre is not None
+                assert head._pre is not None and head.prefetch_hits == 0
                 loss, gx, gy = head.forward_pair(xs.detach(), ys.detach())
+                assert head.prefetch_hits == 1
                 xs.grad, ys.grad = gx, gy
             elif s == 4:    # a stale prefetch (other labels) is discarded without a trace, then the same objects are accepted
                 mine = (xl[sl], yl[sl])
                 head.prefetch(yl[sl].clone(), xl[sl].clone())
                 head.prefetch(*mine)
-                pre = head._pre
                 loss, gx, gy = head.forward_pair(xs.detach(), ys.detach(), *mine)
-                assert pre is not None and head._pre is None and head._last['label'] is pre['ctx']['label']
+                assert head._pre is None and head.prefetch_hits == 2
                 xs.grad, ys.grad = gx, gy
             elif s == 5:    # stale prefetch followed by the autograd entry
                 head.prefetch(yl[sl].clone(), xl[sl].clone())
                 loss = head.forward(xs, ys, xl[sl], yl[sl])
                 loss.backward()
+                assert head._pre is None and head.prefetch_hits == 2
             else:
                 loss = head.forward(xs, ys, xl[sl], yl[sl])
                 loss.backward()

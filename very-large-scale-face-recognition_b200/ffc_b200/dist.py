@@ -235,6 +235,7 @@ class ShardedFFCHead:
         self._timing = [] if (os.environ.get('FFC_DIST_TIMING') and self._nccl) else None
         self._side = torch.cuda.Stream(device=self.dev) if (self._nccl and not os.environ.get('FFC_DIST_NO_OVERLAP')) else None
         self._pre = None            # labels + rollback-pass bookkeeping of the next forward_pair (see prefetch)
+        self.prefetch_hits = 0      # forward_pair calls that consumed prefetched bookkeeping
         # prefetch's collectives get their own communicator: torch's NCCL backend runs all collectives of one process group on one
         # internal stream in issue order, so on the main group they would queue behind the current step's record all-gather /
         # reduce-scatter, i.e. behind the very sweeps they are meant to run under
@@ -391,6 +392,7 @@ class ShardedFFCHead:
             return None
         if (x_label is None and y_label is None) or (x_label is pre['src'][0] and y_label is pre['src'][1]):
             self._pre = None
+            self.prefetch_hits += 1
             return pre
         self._discard_prefetch()
         return None
