@@ -52,6 +52,13 @@ def sweep_traffic(w, world):
     return None
 
 
+def config_of(w, world):
+    """The `config` object of the JSON line: the same for our arm and the reference arm."""
+    return dict(workload=w['name'], rows_per_pass_per_gpu=w['B'], passes_per_step=2, identities=w['N'], queue=w['Q'], feat_dim=w['D'],
+                loss=w['loss_type'], margin=w['margin'], scale=w['scale'], sharding=('none' if world == 1 else f'queue columns /{world}'),
+                l2_policy='working set (bf16 queue %.0f MB per rank) exceeds the 126 MB L2' % (w['Q'] // world * w['D'] * 2 / 1e6))
+
+
 def make_batches(w, n_batches, seed, rank=0, world=1):
     """id half = chunks of a seeded permutation (same ids in x and y), instance halves iid uniform."""
     import torch
@@ -109,7 +116,7 @@ def run_reference(args, w):
     cb, t = cpu_reference(w, max(1, args.steps), max(0, args.warmup))
     line = dict(metric='ffc_head_fwd_bwd_samples_per_s', value=cb['value'], unit='samples/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=w['name'], loss='Arc', margin=w['margin'], scale=w['scale']), cpu_baseline=cb,
+                config=config_of(w, max(1, args.gpus)), cpu_baseline=cb,
                 e2e=dict(value=cb['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -307,9 +314,7 @@ def run_ours(args, w):
         cb, _ = cpu_reference(w, 2, 1) if world == 1 and not args.no_cpu else (None, None)
         line = dict(metric='ffc_head_fwd_bwd_samples_per_s', value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
-                    config=dict(workload=w['name'], rows_per_pass_per_gpu=B, passes_per_step=2, identities=N, queue=Q, feat_dim=D, loss=w['loss_type'],
-                                margin=w['margin'], scale=w['scale'], sharding=('none' if world == 1 else f'queue columns /{world}'),
-                                l2_policy='working set (bf16 queue %.0f MB per rank) exceeds the 126 MB L2' % (q_local * D * 2 / 1e6)),
+                    config=config_of(w, world),
                     e2e=dict(value=samples / (ms_e2e * 1e-3), unit='samples/s', h2d_bytes_per_step=2 * B * D * 4 + 2 * B * 8, d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e / args.steps, last_loss=lv,
                              pipeline='H2D of step k+1 on a copy stream under step k; loss of step k read on the host after step k+1 is enqueued'),
