@@ -45,6 +45,9 @@ def _default_create_net(net_type, **kwargs):
         return NormalizeNet(**kwargs)
     try:  # inside the reference tree this resolves to model/__init__.py:create_net
         from model import create_net as ref_create_net
+        if net_type == 'ir100':   # C4's backbone: defined in the reference (resnet_arcface.py:177) but not registered in its create_net
+            from model.resnet_arcface import iresnet100
+            return iresnet100(**kwargs)
     except ImportError as e:
         raise ValueError(f"net_type {net_type!r}: backbones are outside this package; run inside the reference tree "
                          "(its model/ package on sys.path), pass nn.Module instances via probe_net=/gallery_net=, "
