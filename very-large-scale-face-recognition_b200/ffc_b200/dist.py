@@ -337,7 +337,6 @@ class ShardedFFCHead:
         pass's bookkeeping undoes itself).  Pass CPU tensors (the reference's contract, main.py:59-60): CUDA labels make the
         bookkeeping stream wait for the caller's stream, i.e. no overlap."""
         self._discard_prefetch()
-        B = self.B
         if self._side is None:
             xl_all, yl_all = self._gather_labels(x_label, y_label)
             ctx = self._bookkeep(xl_all, yl_all, False, 0)

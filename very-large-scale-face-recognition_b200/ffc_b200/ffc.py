@@ -14,11 +14,10 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
-import torch.nn.functional as F
 from torch.nn import Module
 
 from . import _capi
-from ._capi import HeadConfig, HeadPass, HeadStats, check, ptr
+from ._capi import HeadConfig, HeadPass, HeadStats, check
 from .lru import LRU
 from .tail import l2_normalize
 
