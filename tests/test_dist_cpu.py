@@ -65,7 +65,7 @@ def _worker(rank, world, port, loss_type, ret):
         from cpu_shard_backend import CpuShardBackend
         from ffc_b200.dist import ShardedFFCHead
         torch.manual_seed(0)
-        D, Q, B, n_ids, steps = 16, 64, 12, 90, 4
+        D, Q, B, n_ids, steps = 16, (64 if world != 3 else 66), 12, 90, 4
         margin = 0.5 if loss_type == 'Arc' else 0.4
         q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64), dim=2)
         Ql = Q // world
@@ -159,8 +159,7 @@ def test_sharded_head_label_prefetch_world2_gloo():
     assert dict(ret) == {0: 'ok', 1: 'ok'}
 
 
-@pytest.mark.parametrize('loss_type', ['AM', 'Arc', 'SV'])
-def test_sharded_head_world2_gloo(loss_type):
+def _run(world, loss_type):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     with socket.socket() as s:
@@ -168,5 +167,17 @@ def test_sharded_head_world2_gloo(loss_type):
         port = s.getsockname()[1]
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, port, loss_type, ret), nprocs=2, join=True)
-    assert dict(ret) == {0: 'ok', 1: 'ok'}
+    mp.spawn(_worker, args=(world, port, loss_type, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: 'ok' for r in range(world)}
+
+
+@pytest.mark.parametrize('loss_type', ['AM', 'Arc', 'SV'])
+def test_sharded_head_world2_gloo(loss_type):
+    _run(2, loss_type)
+
+
+@pytest.mark.parametrize('world,loss_type', [(3, 'Arc'), (4, 'SV')])
+def test_sharded_head_more_ranks_gloo(world, loss_type):
+    """3 ranks (queue 66: shards that are not a power of two) and 4 ranks: candidate sets of several ranks merged per outlier row,
+    target cosines owned by any of them"""
+    _run(world, loss_type)
