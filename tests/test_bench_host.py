@@ -1,0 +1,61 @@
+"""Host-side contract of bench.py (no GPU): synthetic batch composition, the shared `config` object, and the JSON line
+of the reference arm (`--impl reference`: the reference algorithm's CPU port on the host cores)."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_make_batches_follow_the_reference_composition():
+    b = _bench()
+    w = dict(b.WORKLOADS['c3'], B=64, N=5000, D=16)
+    for rank, world in ((0, 1), (1, 4)):
+        batches = b.make_batches(w, 3, seed=1234, rank=rank, world=world)
+        again = b.make_batches(w, 3, seed=1234, rank=rank, world=world)
+        for (x, y, xl, yl), (x2, _, xl2, _) in zip(batches, again):
+            assert torch.equal(x, x2) and torch.equal(xl, xl2)                          # seeded
+            assert x.shape == y.shape == (64, 16) and xl.dtype == torch.int64 and not xl.is_cuda
+            assert torch.allclose(x.norm(dim=1), torch.ones(64), atol=1e-5)             # unit-norm embeddings (ffc.py:157)
+            assert torch.equal(xl[:32], yl[:32]) and len(set(xl[:32].tolist())) == 32   # id half: same ids in x and y, distinct (main.py:58-60)
+            assert int(xl.max()) < 5000 and int(xl.min()) >= 0
+    a = b.make_batches(w, 1, seed=1234, rank=0, world=2)[0]
+    c = b.make_batches(w, 1, seed=1234, rank=1, world=2)[0]
+    assert not set(a[2][:32].tolist()) & set(c[2][:32].tolist())                        # ranks draw different chunks of the permutation
+
+
+def test_config_object_is_shared_by_both_arms():
+    b = _bench()
+    c1, c8 = b.config_of(b.WORKLOADS['c3'], 1), b.config_of(b.WORKLOADS['c3'], 8)
+    assert c1['workload'].startswith('C3') and c1['queue'] == 1 << 20 and c1['identities'] == 1 << 20 and c1['feat_dim'] == 512
+    assert c1['rows_per_pass_per_gpu'] == 1024 and c1['passes_per_step'] == 2 and 'model' not in c1
+    assert c1['sharding'] == 'none' and c8['sharding'] == 'queue columns /8' and 'L2' in c1['l2_policy']
+
+
+def test_reference_arm_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS='4')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'c2', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'ffc_head_fwd_bwd_samples_per_s' and line['unit'] == 'samples/s'
+    assert line['higher_is_better'] is True and line['value'] > 0 and line['vs_baseline'] is None
+    assert line['config'] == _bench().config_of(_bench().WORKLOADS['c2'], 1)
+    cb = line['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == line['value'] and 'queue' in cb['sample']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # a non-zero rank of a torchrun launch exits 0 without work
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=120, env=dict(env, RANK='1', WORLD_SIZE='2'))
+    assert r.returncode == 0 and r.stdout.strip() == ''

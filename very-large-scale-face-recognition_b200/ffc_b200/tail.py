@@ -123,6 +123,10 @@ class FFCTail(nn.BatchNorm1d):
     def forward(self, x, out=None):
         if x.dim() != 2 or x.shape[1] != self.num_features:
             raise ValueError(f'FFCTail expects [batch, {self.num_features}] input, got {tuple(x.shape)}')
+        if not x.is_cuda:       # before any state (num_batches_tracked) is touched
+            raise _capi.FFCError('the FFC tail runs on a CUDA device only (no CPU fallback)')
+        if self.training and x.shape[0] <= 1:
+            raise ValueError(f'Expected more than 1 value per channel when training, got input size {x.size()}')
         use_batch = self.training or self.running_mean is None                   # nn.modules.batchnorm._BatchNorm.forward: bn_training
         momentum = 0.0 if self.momentum is None else self.momentum
         if self.training and self.track_running_stats and self.num_batches_tracked is not None:
