@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the FFC head hot path (BASELINE.json metric: head fwd+bwd samples/s, % of bf16 tensor peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl ours|reference]
 
 A *step* is one reference ``FFC.forward`` over one synthetic batch, embeddings in: a rollback head pass
 (probe=x, gallery=y) plus a commit head pass (probe=y, gallery=x) -- ffc.py:264-267 -- i.e. 2*B probe rows
@@ -9,6 +9,7 @@ A *step* is one reference ``FFC.forward`` over one synthetic batch, embeddings i
 dEmb, both add_margin terms) and, on the rollback pass, the restore.  Workloads:
   c3 (default)  B=1024 rows/GPU, 1,048,576 identities, queue 1,048,576 (column-sharded over N GPUs), D=512, Arc
   c2            B=512, 100k identities, queue 65,536, D=512, Arc (single GPU)
+  c4            B=512 rows/GPU, 10,000,000 identities, queue 1,048,576 (LRU-managed: evictions, unknown labels), D=512, Arc
 `value` is device-timed with the inputs resident in HBM; `e2e` is the same metric through the public
 ``FFCHead.head`` API from pinned host buffers (H2D of embeddings+labels and a D2H read of the loss inside the
 timed region).  `--impl reference` times the reference algorithm's CPU port (oracle/) on the host cores.
@@ -31,6 +32,10 @@ WORKLOADS = {
     'c3': dict(name='C3: FFC head only, 512-d embeddings, batch 1024/GPU, 1M identities, queue 1M', B=1024, N=1 << 20, Q=1 << 20, D=512,
                loss_type='Arc', margin=0.5, scale=32.0),
     'c2': dict(name='C2: FFC head, batch 512, 100k identities, queue 64k, D=512', B=512, N=100000, Q=65536, D=512,
+               loss_type='Arc', margin=0.5, scale=32.0),
+    # head of C4 (the backbone is outside the path): ten identities per queue slot, so instance rows mostly miss (LRU eviction path)
+    # and most probe labels of the instance half are unknown (hard-negative rows).  Not the default; not measured in round 1.
+    'c4': dict(name='C4 head: batch 512/GPU, 10M identities, LRU-managed queue 1M, D=512', B=512, N=10_000_000, Q=1 << 20, D=512,
                loss_type='Arc', margin=0.5, scale=32.0),
 }
 CPU_SAMPLE = dict(B=256, Q=32768)   # bounded CPU sample: rows per pass and queue slice; scaled linearly in Q
