@@ -159,6 +159,63 @@ def test_sharded_head_label_prefetch_world2_gloo():
     assert dict(ret) == {0: 'ok', 1: 'ok'}
 
 
+def _worker_merged(rank, world, port, loss_type, ret):
+    """tests/proto_merged_exchange.py: one exchange point per step; results must equal the dense oracle, and must NOT without the overlay"""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from proto_merged_exchange import CpuShardBackend2, MergedShardedHead
+        torch.manual_seed(0)
+        # few identities, small queue: in-batch duplicates, evictions, targets and hard negatives inside the rows both passes overwrite
+        D, Q, B, n_ids, steps = 16, 32, 12, 40, 6
+        margin = 0.5 if loss_type == 'Arc' else 0.4
+        q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64), dim=2)
+        mk = lambda ov: MergedShardedHead(D, Q, 32.0, loss_type, margin, max_batch=B, use_overlay=ov,
+                                          backend_factory=lambda ql, off, n: CpuShardBackend2(D, ql, Q, off, n, 32.0, loss_type, margin, hard_neg_k(Q),
+                                                                                              queue=q0[:, off:off + ql]))
+        head, naive = mk(True), mk(False)
+        oracle = ShardedOracle(world, D, Q, 32.0, loss_type, margin, queue=q0, dtype=torch.float64)
+        gen = torch.Generator().manual_seed(9)
+        cen = F.normalize(torch.randn(n_ids, D, generator=gen, dtype=torch.float64))
+        naive_wrong = 0
+        for s in range(steps):
+            xl = torch.randint(0, n_ids, (world * B,), generator=gen)
+            yl = torch.cat([xl[:world * B // 2], torch.randint(0, n_ids, (world * B - world * B // 2,), generator=gen)])
+            x = F.normalize(cen[xl] + 0.4 * torch.randn(world * B, D, generator=gen, dtype=torch.float64))
+            y = F.normalize(cen[yl] + 0.4 * torch.randn(world * B, D, generator=gen, dtype=torch.float64))
+            sl = slice(rank * B, (rank + 1) * B)
+            loss, dx, dy = head.forward_pair(x[sl], y[sl], xl[sl], yl[sl])
+            _, dx_n, dy_n = naive.forward_pair(x[sl], y[sl], xl[sl], yl[sl])
+            xo, yo = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            ref = oracle.forward(xo, yo, xl.tolist(), yl.tolist())
+            ref.backward()
+            assert abs(float(loss) - float(ref)) <= 1e-9 * abs(float(ref)), (s, float(loss), float(ref))
+            assert torch.allclose(dx, xo.grad[sl], rtol=1e-8, atol=1e-12), s
+            assert torch.allclose(dy, yo.grad[sl], rtol=1e-8, atol=1e-12), s
+            assert head.backend.lru.state_dict() == oracle.lrus[rank].state_dict()
+            assert torch.allclose(head.backend.queue, oracle.queue[:, rank * (Q // world):(rank + 1) * (Q // world)].double(), atol=0, rtol=0)
+            naive_wrong += int(not torch.allclose(dx_n, xo.grad[sl], rtol=1e-8, atol=1e-12))
+        t = torch.tensor([naive_wrong, head.backend.overlay_reads])
+        dist.all_reduce(t)
+        assert int(t[0]) > 0 and int(t[1]) > 0, t.tolist()       # the overlay was needed, and it was read
+        ret[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('loss_type', ['Arc', 'SV'])
+def test_merged_exchange_prototype(loss_type):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_merged, args=(2, port, loss_type, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: 'ok', 1: 'ok'}
+
+
 def _run(world, loss_type):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
