@@ -227,3 +227,12 @@ class CpuShardBackend:
 
     def end_pass(self):
         pass
+
+    def export_state(self):
+        return dict(lru=self.lru.ref.state_dict(), queue=self.queue.clone(), qpos=list(self.qpos))
+
+    def import_state(self, st):
+        self.lru = _LruShim(self.Ql)
+        self.lru.ref.restore([(int(k), int(v)) for k, v in st['lru']])
+        self.queue = st['queue'].double().clone()
+        self.qpos = [int(v) for v in st['qpos']]

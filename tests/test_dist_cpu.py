@@ -147,6 +147,70 @@ def _worker_prefetch(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def _worker_resume(rank, world, port, ret):
+    """ShardedFFCHead.checkpoint() / load_checkpoint(): a head resumed from the per-rank snapshot continues exactly like the original
+    (through torch.save / torch.load, i.e. the file a trainer would write)"""
+    import io
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from cpu_shard_backend import CpuShardBackend
+        from ffc_b200.dist import ShardedFFCHead
+        D, Q, B, n_ids = 16, 64, 12, 90
+        q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64, generator=torch.Generator().manual_seed(3)), dim=2)
+        mk = lambda q: ShardedFFCHead(D, Q, 32.0, 'AM', 0.4, max_batch=B,
+                                      backend_factory=lambda ql, off, n: CpuShardBackend(D, ql, Q, off, n, 32.0, 'AM', 0.4, hard_neg_k(Q),
+                                                                                         queue=q[:, off:off + ql]))
+        gen = torch.Generator().manual_seed(11 + rank)
+        cen = F.normalize(torch.randn(n_ids, D, generator=torch.Generator().manual_seed(12), dtype=torch.float64))
+
+        def batch():
+            xl = torch.randint(0, n_ids, (B,), generator=gen)
+            yl = torch.cat([xl[:B // 2], torch.randint(0, n_ids, (B - B // 2,), generator=gen)])
+            return (F.normalize(cen[xl] + 0.4 * torch.randn(B, D, generator=gen, dtype=torch.float64)),
+                    F.normalize(cen[yl] + 0.4 * torch.randn(B, D, generator=gen, dtype=torch.float64)), xl, yl)
+        a = mk(q0)
+        for _ in range(3):
+            a.forward_pair(*batch())
+        a.prefetch(*batch()[2:])                     # a pending prefetch must not leak into the snapshot
+        buf = io.BytesIO()
+        torch.save(a.checkpoint(), buf)
+        buf.seek(0)
+        ck = torch.load(buf, weights_only=False)
+        assert set(ck) == {'lru', 'fc', 'qp', 'shard'} and ck['shard'] == (rank, world, Q) and tuple(ck['fc'].shape) == (2, Q // world, D)
+        assert all(0 <= s < Q // world for _, s in ck['lru']) and all(k % world == rank for k, _ in ck['lru'])
+        b = mk(torch.zeros_like(q0))                 # wrong queue, empty LRU: everything must come from the snapshot
+        b.load_checkpoint(ck)
+        for _ in range(2):
+            bt = batch()
+            ra, rb = a.forward_pair(*bt), b.forward_pair(*bt)
+            for u, v in zip(ra, rb):
+                assert torch.equal(u, v)
+            assert a.backend.lru.state_dict() == b.backend.lru.state_dict() and a.backend.qpos == b.backend.qpos
+            assert torch.equal(a.backend.queue, b.backend.queue)
+        wrong = dict(ck, shard=((rank + 1) % world, world, Q))
+        try:
+            b.load_checkpoint(wrong)
+            raise RuntimeError('a snapshot of another shard was accepted')
+        except AssertionError:
+            pass
+        ret[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_head_checkpoint_resume_world2_gloo():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_resume, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: 'ok', 1: 'ok'}
+
+
 def test_sharded_head_label_prefetch_world2_gloo():
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

@@ -183,6 +183,18 @@ class CudaShardBackend:
     def end_pass(self):
         self.cmask.zero_()
 
+    # -- checkpoint of the shard (host-sync) ------------------------------------------------------
+    def export_state(self):
+        return dict(lru=self.lru.state_dict(), queue=self.queue.detach().cpu(), qpos=self.qpos.cpu().tolist())
+
+    def import_state(self, st):
+        assert tuple(st['queue'].shape) == tuple(self.queue.shape), (tuple(st['queue'].shape), tuple(self.queue.shape))
+        self.lru.clear()
+        self.lru.restore([(int(k), int(v)) for k, v in st['lru']])
+        self.queue.copy_(st['queue'].to(self.dev))
+        self.sync_mirror()
+        self.qpos.copy_(torch.tensor([int(v) for v in st['qpos']], dtype=torch.uint8).to(self.dev))
+
     def set_timing(self, enable):
         check(self.lib.ffc_head_set_timing(self._h, 1 if enable else 0))
 
@@ -545,6 +557,27 @@ class ShardedFFCHead:
         self._mark('restore')
         self._last = dict(label=label, n_mine=ctx['n_mine'])
         return loss, dp
+
+    # -- checkpoint / resume: one dict per rank, the reference's wire format (main.py:84-85) for the rank's shard -----------------
+    def checkpoint(self):
+        """``{'lru': [(key, local slot)] most -> least recently used (lru.py:102-108), 'fc': the rank's [2, Q/R, D] queue rows on the
+        CPU, 'qp': {local slot: 0 / 1} (ffc.py:41-43), 'shard': (rank, ranks, queue_size)}`` -- what main.py:85 saves, per shard: the
+        recency order of a sharded LRU exists per shard only (each is the reference LRU(Q/R) of the identities it owns).  Save one
+        file per rank; resume with the same number of ranks."""
+        self._discard_prefetch()
+        if self._side is not None:
+            self._side.synchronize()
+        st = self.backend.export_state()
+        return {'lru': st['lru'], 'fc': st['queue'], 'qp': dict(enumerate(st['qpos'])), 'shard': (self.rank, self.R, self.Q)}
+
+    def load_checkpoint(self, ckpt):
+        assert tuple(ckpt['shard']) == (self.rank, self.R, self.Q), f"checkpoint of shard {tuple(ckpt['shard'])}, this is {(self.rank, self.R, self.Q)}"
+        self._discard_prefetch()
+        if self._side is not None:
+            self._side.synchronize()
+        self.backend.import_state(dict(lru=ckpt['lru'], queue=ckpt['fc'], qpos=[ckpt['qp'][i] for i in range(self.Ql)]))
+        if self._side is not None:      # the bookkeeping stream must see the imported state
+            torch.cuda.current_stream(self.dev).synchronize()
 
     def head_pass_gathered(self, p_all, g_all, pl_all, gl_all, commit):
         ctx = self._bookkeep(pl_all, gl_all, commit, 0)
