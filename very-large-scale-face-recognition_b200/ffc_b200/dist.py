@@ -254,9 +254,7 @@ class ShardedFFCHead:
         self._side_group = None
         if self._side is not None:
             ranks = dist.get_process_group_ranks(group) if group is not None else None
-            self._side_group = dist.new_group(ranks=ranks, backend='nccl')
-            # create its communicator now (NCCL communicators are built on first use), not inside somebody's first training step
-            dist.all_reduce(torch.zeros(1, device=self.dev), group=self._side_group)
+            self._side_group = dist.new_group(ranks=ranks, backend='nccl')      # its communicator is built on first use (first prefetch)
         self._rb_done = None        # event: the last pass that used bookkeeping set 0 has finished with it
         self._lru_main_ev = None    # event: the last bookkeeping enqueued on the caller's stream (the LRU state prefetch builds on)
 
