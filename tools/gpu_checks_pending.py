@@ -5,8 +5,8 @@
     torchrun --nproc-per-node 2 tools/gpu_checks_pending.py --dist                   # two GPUs: sharded checkpoint / resume, all-hit probe
 
 One GPU:  (1) the C1-shaped fixtures (tests/golden/c1_*.npz) through the CUDA head, fp32 check mode (1e-5) and bf16 (1e-2), bookkeeping and
-final queue bit-exact;  (2) ffc_b200.train on a toy backbone ending in FFCTail: a few steps, loss finite and decreasing bookkeeping sane,
-snapshot written and resumed;  (3) bench workload c4 is `python bench.py --workload c4` (not run from here).
+final queue bit-exact;  (2) ffc_b200.train on a toy backbone ending in FFCTail: 12 steps, finite losses, snapshots written in the
+reference's format and resumed;  (3) bench workload c4 is `python bench.py --workload c4` (not run from here).
 Prints one line per check and exits non-zero on the first failure.  Each passing check should then move into tests/ as an `-m gpu` test."""
 import argparse
 import glob
