@@ -201,7 +201,7 @@ typedef struct ffc_head_config {
   int64_t q_local;       /* queue rows (slots) held by this rank */
   int64_t q_total;       /* global queue size (== q_local on one GPU) */
   int64_t col_offset;    /* global slot index of local row 0 */
-  int32_t feat_dim;      /* D: multiple of 64, <= 512 for the bf16 path */
+  int32_t feat_dim;      /* D: 64, 128, 256 or 512 for the bf16 path; any multiple of 4 up to 512 in check mode */
   int32_t loss_type;     /* FFC_LOSS_* */
   float scale;           /* ffc.py:34 */
   float margin;          /* ffc.py:35 */

@@ -119,3 +119,18 @@ def test_tail_module_is_a_batchnorm1d():
             net.features(torch.randn(4, 32))                          # no CPU fallback
         with pytest.raises(ffc_b200.FFCError):
             ffc_b200.l2_normalize(torch.randn(4, 32))
+
+
+def test_head_create_rejects_unsupported_widths_up_front():
+    """argument validation precedes any device work: widths the tensor-core sweep is not built for fail at create, with the reason"""
+    import ctypes as C
+    from ffc_b200 import _capi
+    lib = _capi.lib()
+    h = C.c_void_p()
+    for D, prec, frag in ((192, 0, b'64, 128, 256 or 512'), (130, 1, b'multiple of 4'), (1024, 1, b'<= 512')):
+        cfg = _capi.HeadConfig(64, 1024, 1024, 0, D, 0, 32.0, 0.4, 3, prec)
+        assert lib.ffc_head_create(C.byref(cfg), C.byref(h)) == 1 and frag in lib.ffc_last_error(), (D, lib.ffc_last_error())
+    cfg = _capi.HeadConfig(64, 1024, 1024, 0, 128, 0, 64.0, 0.4, 3, 0)          # scale + fixed max must stay below 87 (fp32 exp range)
+    assert lib.ffc_head_create(C.byref(cfg), C.byref(h)) == 1 and b'scale' in lib.ffc_last_error()
+    cfg = _capi.HeadConfig(64, 1024, 1024, 0, 128, 0, 32.0, 0.4, 11, 0)          # ffc.py:48: hard_neg <= 10
+    assert lib.ffc_head_create(C.byref(cfg), C.byref(h)) == 1 and b'topk' in lib.ffc_last_error()

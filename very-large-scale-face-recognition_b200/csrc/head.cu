@@ -893,7 +893,9 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_REQUIRE(cfg->topk >= 1 && cfg->topk <= KMAX, "ffc_head_create: topk %d outside [1,%d]", cfg->topk, KMAX);
   FFC_REQUIRE(cfg->precision == FFC_PREC_BF16 || cfg->precision == FFC_PREC_FP32, "ffc_head_create: precision %d", cfg->precision);
   if (cfg->precision == FFC_PREC_BF16) {
-    FFC_REQUIRE(cfg->feat_dim % 64 == 0, "ffc_head_create: the bf16 tensor-core path needs feat_dim %% 64 == 0 (got %d)", cfg->feat_dim);
+    FFC_REQUIRE(cfg->feat_dim == 64 || cfg->feat_dim == 128 || cfg->feat_dim == 256 || cfg->feat_dim == 512,
+                "ffc_head_create: the bf16 tensor-core path is built for feat_dim 64, 128, 256 or 512 (got %d); other widths: FFC_PREC_FP32",
+                cfg->feat_dim);
     // exp(s*z - M) must stay a normal float: range 2*M
     FFC_REQUIRE(cfg->scale + fixed_max_of(*cfg) < 87.f, "ffc_head_create: scale %.1f too large for the fixed-max softmax (scale + M must be < 87)", cfg->scale);
   }
