@@ -12,7 +12,8 @@ dEmb, both add_margin terms) and, on the rollback pass, the restore.  Workloads 
   c4            B=512 rows/GPU, 10,000,000 identities, queue 1,048,576 (LRU-managed: evictions, unknown labels), D=512, Arc
 `value` is device-timed with the inputs resident in HBM; `e2e` is the same metric through the public
 ``FFCHead.head`` API from pinned host buffers (H2D of embeddings+labels and a D2H read of the loss inside the
-timed region).  `--impl reference` times the reference algorithm's CPU port (oracle/) on the host cores.
+timed region).  `--impl reference` times the reference's own head (unmodified ffc.py / lru.py, staged under oracle/_ref by
+oracle/make_ref.py; the oracle port only if neither /root/reference nor the staging exists) on all host cores, on a bounded sample.
 """
 from __future__ import annotations
 
@@ -38,7 +39,7 @@ WORKLOADS = {
     'c4': dict(name='C4 head: batch 512/GPU, 10M identities, LRU-managed queue 1M, D=512', B=512, N=10_000_000, Q=1 << 20, D=512,
                loss_type='Arc', margin=0.5, scale=32.0),
 }
-CPU_SAMPLE = dict(B=256, Q=32768)   # bounded CPU sample: rows per pass and queue slice; scaled linearly in Q
+CPU_SAMPLE = dict(B=1024, Q=32768)   # bounded CPU sample: rows per pass (the workload's own, up to 1024) and queue slice; scaled linearly in Q
 
 
 def peaks():
@@ -85,33 +86,114 @@ def make_batches(w, n_batches, seed, rank=0, world=1):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline: the reference algorithm's port (oracle/head_ref.py) on the host cores, bounded sample
+# CPU baseline: the reference's own head (ffc.py / lru.py, unmodified, through oracle/ref_shim.py: /root/reference in the build
+# container, the byte-for-byte staging oracle/_ref on the GPU box) on the host cores; the oracle port only where neither exists.
+# Bounded sample: the workload's full rows per pass against a SLICE of the queue; per-sample cost is linear in the queue size
+# (blend, both GEMMs, softmax; the argsort is Q log Q), so samples/s at the full queue = sample figure * Qs / Q -- an extrapolation
+# that favours the CPU, and is labelled as such in the reference arm's `config`.
 # --------------------------------------------------------------------------------------------------
-def cpu_reference(w, steps, warmup):
+def host_threads():
+    """All the host threads the CPU arm can use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it)."""
     import torch
-    from oracle.head_ref import HeadOracle
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
+def sample_of(w):
     Bs, Qs = min(CPU_SAMPLE['B'], w['B']), min(CPU_SAMPLE['Q'], w['Q'])
-    ws = dict(w, B=Bs, N=max(Qs, int(w['N'] * Qs / w['Q'])), Q=Qs)
-    o = HeadOracle(w['D'], Qs, w['scale'], w['loss_type'], w['margin'], dtype=torch.float32)
-    o.lru.restore([(i, i) for i in range(Qs)])
-    batches = make_batches(ws, 4, seed=1234)
-    times = []
-    for s in range(warmup + steps):
-        x, y, xl, yl = batches[s % len(batches)]
+    return dict(w, B=Bs, N=max(Qs, int(w['N'] * Qs / w['Q'])), Q=Qs)
+
+
+def cpu_head_runner(ws):
+    """-> (kind, step(x, y, xl, yl)) for one FFC.forward + backward on the CPU at shape `ws`, LRU pre-filled (steady state)."""
+    import torch
+    from oracle import ref_shim
+    if ref_shim.available():
+        m = ref_shim.make_ffc(ws['D'], ws['Q'], ws['scale'], ws['loss_type'], ws['margin'])
+        m.lru.restore([(i, i) for i in range(ws['Q'])])
+
+        def step(x, y, xl, yl):
+            return ref_shim.forward_backward(m, x, y, xl, yl)[0]
+        return 'reference', step
+    from oracle.head_ref import HeadOracle
+    o = HeadOracle(ws['D'], ws['Q'], ws['scale'], ws['loss_type'], ws['margin'], dtype=torch.float32)
+    o.lru.restore([(i, i) for i in range(ws['Q'])])
+
+    def step(x, y, xl, yl):
         x = x.clone().requires_grad_(True)
         y = y.clone().requires_grad_(True)
-        t0 = time.perf_counter()
         loss = o.forward(x, y, xl.tolist(), yl.tolist())
         loss.backward()
+        return float(loss)
+    return 'port', step
+
+
+def time_cpu(ws, steps, warmup, seed=1234, budget_s=60.0):
+    """Mean seconds per step over up to `steps` timed steps; stops early (after >= 2) once `budget_s` of timed work is spent, so that
+    the CPU arm ends within minutes whatever --steps says."""
+    kind, step = cpu_head_runner(ws)
+    batches = make_batches(ws, min(4, steps + warmup), seed=seed)
+    times = []
+    for s in range(warmup + steps):
+        b = batches[s % len(batches)]
+        t0 = time.perf_counter()
+        step(*b)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
-    t = sum(times) / len(times)
+            if len(times) >= 2 and sum(times) > budget_s:
+                break
+    return kind, sum(times) / len(times)
+
+
+def cpu_reference(w, steps, warmup):
+    import torch
+    cores = host_threads()
+    ws = sample_of(w)
+    kind, t = time_cpu(ws, steps, warmup)
+    Bs, Qs = ws['B'], ws['Q']
     raw = 2 * Bs / t                               # samples/s at the sample's queue size
     scaled = raw * Qs / w['Q']                     # per-sample cost is linear in Q
-    sample = (f'oracle port (torch fp32, materialised B x Q logits, argsort top-k, autograd backward) on B={Bs} rows/pass, '
-              f'queue {Qs}, D={w["D"]}: {t * 1e3:.0f} ms/step = {raw:.0f} samples/s, scaled by {Qs}/{w["Q"]} to the full queue')
-    return dict(value=scaled, unit='samples/s', cores=torch.get_num_threads(), kind='port', sample=sample), t
+    what = ('the unmodified reference head (ffc.py FFC.forward + backward, lru.py; fp32 CPU, normalise-only backbones)' if kind == 'reference'
+            else 'oracle port (torch fp32, materialised B x Q logits, argsort top-k, autograd backward)')
+    sample = (f'{what} on B={Bs} rows/pass, queue {Qs}, D={w["D"]}: {t * 1e3:.0f} ms/step = {raw:.0f} samples/s'
+              + (f', scaled by {Qs}/{w["Q"]} to the full queue (extrapolated)' if Qs != w['Q'] else ' (full configuration, not extrapolated)'))
+    cb = dict(value=scaled, unit='samples/s', cores=cores, kind=kind, sample=sample, sample_rows_per_pass=Bs, sample_queue=Qs,
+              extrapolated=bool(Qs != w['Q'] or Bs != w['B']), torch=torch.__version__)
+    return cb, t
+
+
+def cpu_extras():
+    """BASELINE.json configs[0] (C1: the reference's own CPU-runnable case, head shape batch 64 / 10k identities / queue 4096, D = 128 and
+    512) timed IN FULL on the host cores, and the Python LRU's get() rate: the LRU baseline."""
+    out = {}
+    for D in (128, 512):
+        ws = dict(name='C1', B=64, N=10000, Q=4096, D=D, loss_type='Arc', margin=0.5, scale=32.0)
+        kind, t = time_cpu(ws, 10, 2, seed=77)
+        out[f'c1_head_d{D}'] = dict(samples_per_s=2 * 64 / t, ms_per_step=t * 1e3, kind=kind, extrapolated=False,
+                                    shape='B=64 rows/pass, 10k identities, queue 4096, Arc, fp32')
+    from oracle import ref_shim
+    if ref_shim.available():
+        lru_cls, lk = ref_shim.load()[1].LRU, 'reference'
+    else:
+        from oracle.lru_ref import LRU as lru_cls
+        lk = 'port'
+    import random
+    rng = random.Random(0)
+    lru = lru_cls(65536)
+    keys = [rng.randrange(1 << 20) for _ in range(400000)]
+    for k in keys[:100000]:
+        lru.get(k)
+    t0 = time.perf_counter()
+    for k in keys[100000:]:
+        lru.get(k)
+    dt = time.perf_counter() - t0
+    out['lru_get'] = dict(keys_per_s=300000 / dt, kind=lk, cores=1, shape='capacity 65536, uniform keys over 2^20 (94 % misses -> evictions)')
+    return out
 
 
 def run_reference(args, w):
@@ -119,9 +201,12 @@ def run_reference(args, w):
     if rank != 0:
         return
     cb, t = cpu_reference(w, max(1, args.steps), max(0, args.warmup))
+    cfg = dict(config_of(w, max(1, args.gpus)),
+               reference_sample=dict(rows_per_pass=cb['sample_rows_per_pass'], queue=cb['sample_queue'], extrapolated=cb['extrapolated'],
+                                     rule='samples/s measured on the sample, multiplied by sample queue / full queue (cost per sample is linear in the queue size)'))
     line = dict(metric='ffc_head_fwd_bwd_samples_per_s', value=cb['value'], unit='samples/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=config_of(w, max(1, args.gpus)), cpu_baseline=cb,
+                config=cfg, cpu_baseline=cb,
                 e2e=dict(value=cb['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -173,6 +258,71 @@ class Clocks:
 
 
 # --------------------------------------------------------------------------------------------------
+# the HBM-bound kernels of the path, each timed alone (CUDA events on the launch stream, 50 launches after 5 warm-ups): achieved GB/s =
+# ALGORITHMIC bytes / time, against the measured copy bandwidth.  They are latency-bound by construction (a few KB to a
+# few MB per launch); the figure that matters is microseconds per batch and keys/s.
+# --------------------------------------------------------------------------------------------------
+def kernel_micro(head, w, dev, world):
+    import torch
+    import ctypes as C
+    from ffc_b200 import _capi
+    lib, pk = _capi.lib(), peaks()
+    B, Q, D, N = w['B'], w['Q'], w['D'], w['N']
+    g = torch.Generator().manual_seed(99)
+    s = torch.cuda.current_stream(dev).cuda_stream
+
+    def timed(fn, n=50, warm=5):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n * 1e3            # microseconds per launch group
+
+    out = {}
+    lru, qpos = head._lru, head.qpos
+    keys = [torch.randint(0, N, (B,), generator=g).to(dev) for _ in range(8)]
+    cols, rows = torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev)
+    ones, n_ones = torch.empty(B, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+    cmask = torch.zeros((Q + 31) // 32 + 1, dtype=torch.int32, device=dev)
+    it = [0]
+
+    def lru_rollback():       # try_get x B + undo: the LRU side of a rollback pass, state unchanged afterwards
+        k = keys[it[0] % 8]
+        it[0] += 1
+        n_ones.zero_()
+        lru.assign(k, journal=True, qpos=qpos, rows=rows, cols=cols, ones_list=ones, n_ones=n_ones, cmask=cmask)
+        lru.undo(B, qpos)
+    us = timed(lru_rollback)
+    by = 41.0 * B * 2                                    # ~41 B / key algorithmic (key, table entry, recency, outputs), assign + undo
+    out['lru_try_get_plus_undo'] = dict(us_per_batch=us, keys_per_s=B / (us * 1e-6), achieved_gbs=by / (us * 1e-6) / 1e9, peak_gbs=pk['hbm'],
+                                        frac=by / (us * 1e-6) / 1e9 / pk['hbm'], algorithmic_bytes=by, keys=B)
+    lab = torch.empty(B, dtype=torch.int32, device=dev)
+    us = timed(lambda: lru.view_batch(keys[0], lab))
+    by = 28.0 * B
+    out['lru_view'] = dict(us_per_batch=us, keys_per_s=B / (us * 1e-6), achieved_gbs=by / (us * 1e-6) / 1e9, peak_gbs=pk['hbm'],
+                           frac=by / (us * 1e-6) / 1e9 / pk['hbm'], algorithmic_bytes=by, keys=B)
+    cmask.zero_()
+    # enqueue scatter + restore (the rollback pass's pair): B rows of D floats into random distinct slots
+    r = torch.zeros(B, dtype=torch.int32, device=dev)
+    c = torch.randperm(Q, generator=g)[:B].to(torch.int32).to(dev)
+    gl = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(dev)
+    undo = torch.empty(B, D, device=dev)
+
+    def scatter_restore():
+        _capi.check(lib.ffc_queue_scatter(head.queue.data_ptr(), head.queue_bf16.data_ptr(), r.data_ptr(), c.data_ptr(), gl.data_ptr(), B, Q, D, undo.data_ptr(), s))
+        _capi.check(lib.ffc_queue_restore(head.queue.data_ptr(), head.queue_bf16.data_ptr(), r.data_ptr(), c.data_ptr(), undo.data_ptr(), B, Q, D, s))
+    us = timed(scatter_restore)
+    by = float(B * D * (4 + 4 + 2 + 8) + B * D * (4 + 4 + 2))       # scatter with undo (read g, old row; write row, undo, mirror) + restore
+    out['queue_scatter_plus_restore'] = dict(us_per_batch=us, rows_per_s=B / (us * 1e-6), achieved_gbs=by / (us * 1e-6) / 1e9, peak_gbs=pk['hbm'],
+                                             frac=by / (us * 1e-6) / 1e9 / pk['hbm'], algorithmic_bytes=by, rows=B)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args, w):
@@ -220,7 +370,6 @@ def run_ours(args, w):
     # exactly 1, the reference's Arc NaN hazard
     n_b = args.steps + args.warmup
     host = make_batches(w, n_b, seed=1234, rank=rank, world=world)
-    pinned = [tuple(t.pin_memory() for t in b) for b in host]
     # sharded head: labels stay on the host (pinned), as in the reference's loop; one GPU: device-resident
     devb = [(x.to(dev), y.to(dev), xl.pin_memory() if world > 1 else xl.to(dev), yl.pin_memory() if world > 1 else yl.to(dev)) for x, y, xl, yl in host]
 
@@ -256,7 +405,10 @@ def run_ours(args, w):
     loss_val = float(loss)
 
     # ---- end to end through the public API from pinned host buffers (e2e) ----
-    pinned = pinned[::-1]     # other embeddings than the ones just enqueued
+    # fresh batches (other embeddings AND other identities' rows than the ones just enqueued: a re-fed embedding makes its target
+    # cosine exactly 1 -- the Arc clamp regime -- and the loss would not be comparable with the device-timed phase)
+    del pinned
+    pinned = [tuple(t.pin_memory() for t in b) for b in make_batches(w, n_b, seed=4321, rank=rank, world=world)]
     phase_ms = head.phase_times() if getattr(head, '_timing', None) else None
     if phase_ms is not None:
         head._timing = None
@@ -315,6 +467,11 @@ def run_ours(args, w):
     q_local = Q // world
     flops = 4.0 * rows_per_sweep * q_local * D                     # algorithmic FLOPs of one main sweep launch (4*B*Q*D)
     ach = flops * sweep_n / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
+    # the burst figure for a kernel timed in a short region, the sustained one when the timed region is long enough for the board to
+    # settle at its power cap (MEASURED_PEAKS.json: best of 10 vs back to back for 4 s)
+    long_run = ms >= 2000.0
+    peak = pk['sustained'] if long_run else pk['burst']
+    aux = kernel_micro(head, w, dev, world) if (world == 1 and not args.no_aux) else None
     if rank == 0:
         cb, _ = cpu_reference(w, 2, 1) if world == 1 and not args.no_cpu else (None, None)
         line = dict(metric='ffc_head_fwd_bwd_samples_per_s', value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -324,13 +481,18 @@ def run_ours(args, w):
                              ms_per_step=ms_e2e / args.steps, last_loss=lv,
                              pipeline='H2D of step k+1 on a copy stream under step k; loss of step k read on the host after step k+1 is enqueued'),
                     gpu_launches=int(launches),
-                    roofline=dict(bound='tensor', achieved=ach, peak=pk['sustained'], unit='TFLOP/s', frac=ach / pk['sustained'], traffic=sweep_traffic(w, world),
+                    roofline=dict(bound='tensor', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak, traffic=sweep_traffic(w, world),
                                   kernel='ffc_head_sweep_sm100_kernel (main sweep)', launches=int(sweep_n), avg_ms=sweep_ms / max(1, sweep_n),
-                                  algorithmic_flops_per_launch=flops, peak_kind=f'bf16_tflops_sustained ({pk["src"]})',
-                                  frac_of_burst=ach / pk['burst'], sweep_share_of_step=sweep_ms / ms),
+                                  algorithmic_flops_per_launch=flops,
+                                  peak_kind=('bf16_tflops_sustained' if long_run else 'bf16_tflops (burst)') + f' ({pk["src"]}; timed region {ms / 1e3:.2f} s)',
+                                  frac_of_burst=ach / pk['burst'], frac_of_sustained=ach / pk['sustained'], sweep_share_of_step=sweep_ms / ms),
                     clocks=clk, loss=loss_val)
         if cb is not None:
             line['cpu_baseline'] = cb
+        if aux is not None:
+            line['hbm_kernels'] = aux
+        if world == 1 and not args.no_cpu:
+            line['cpu_extras'] = cpu_extras()
         if world > 1 and os.environ.get('FFC_DIST_TIMING'):
             line['phase_ms_total'] = phase_ms
         print(json.dumps(line))
@@ -346,6 +508,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-aux', action='store_true', help='skip the per-kernel HBM micro timings')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == 'reference':

@@ -36,7 +36,8 @@ extern "C" {
 #define FFC_PREC_BF16 0 /* tcgen05 bf16 tensor-core sweep (fp32 accumulate in TMEM)            */
 #define FFC_PREC_FP32 1 /* check mode: fp32 inputs, fp64 accumulate, SIMT, no tensor cores     */
 
-#define FFC_LRU_MAX_BATCH 1024 /* keys per ffc_lru_assign call (callers chunk larger batches) */
+#define FFC_LRU_MAX_BATCH 1024 /* keys the single resolve CTA replays per chunk of a batch */
+#define FFC_LRU_MAX_KEYS 65536 /* keys per ffc_lru_assign call (one launch pair; callers split larger batches) */
 #define FFC_TOPK_MAX 10        /* ffc.py:48 hard_neg <= 10 */
 
 const char* ffc_last_error(void);
@@ -70,10 +71,12 @@ int ffc_lru_clear(ffc_lru_t* h, void* stream);
  * ffc.py:165,176 `ones_idx`.  qpos_dev (uint8[capacity]) is ffc.py:41-43 queue_position_dict; pass
  * NULL for a plain LRU (rows_out is then 0 for misses and 1 for hits... unspecified; pass NULL too).
  * Any of rows_out, hit_out, ones_list_dev, n_ones_dev, cmask_dev may be NULL.
- * 1 <= n <= FFC_LRU_MAX_BATCH.  n_ones_dev is accumulated (caller zeroes it).
+ * 1 <= n <= FFC_LRU_MAX_KEYS: one lookup launch + one resolve launch whatever n is (the resolve CTA walks the batch in chunks
+ * of FFC_LRU_MAX_BATCH keys); ring / table space for all n accesses is reserved before the first one.  n_ones_dev is
+ * accumulated (caller zeroes it).
  * n_dev (optional device scalar) / n_base: when the number of keys is only known on the device (a rank's
  * share of an all-gathered batch), the call processes keys [0, clamp(*n_dev - n_base, 0, n)) and leaves the
- * outputs of the remaining positions untouched; pass NULL, 0 otherwise. */
+ * outputs of the remaining positions untouched (the resolve CTA stops after the last non-empty chunk); pass NULL, 0 otherwise. */
 int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int journal, uint8_t* qpos_dev,
                    int32_t* rows_out, int32_t* cols_out, uint8_t* hit_out, int32_t* ones_list_dev,
                    int32_t* n_ones_dev, uint32_t* cmask_dev, const int32_t* n_dev, int n_base, void* stream);

@@ -1,9 +1,11 @@
 """Loader for the UNMODIFIED reference head (/root/reference/{ffc,lru}.py) as a CPU oracle.
 
-TEST INFRASTRUCTURE ONLY and only usable where /root/reference exists (the build
-container) -- it is what tests/golden/make_golden.py uses to produce the committed
-fixtures, and what tests/test_oracle_vs_reference.py uses for live cross-checks.
-Nothing on the GPU box may import it (the reference does not travel).
+TEST INFRASTRUCTURE ONLY.  In the build container it loads /root/reference -- it is what
+tests/golden/make_golden.py uses to produce the committed fixtures, and what
+tests/test_oracle_vs_reference.py uses for live cross-checks.  On the GPU box, where
+/root/reference does not exist, it loads the byte-for-byte staging oracle/_ref/ written by
+oracle/make_ref.py (git-ignored, shipped with the snapshot): bench.py's cpu_baseline /
+--impl reference legs and the -m gpu tests that run the reference's own backbones.
 
 No reference file is edited or copied; three process-local shims make the head
 runnable on CPU:
@@ -25,7 +27,16 @@ import sys
 import torch
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get('FFC_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')     # oracle/make_ref.py: byte-for-byte staging for the GPU box
+
+
+def _default_root():
+    if os.path.isfile('/root/reference/ffc.py'):
+        return '/root/reference'
+    return _STAGED
+
+
+REF_ROOT = os.environ.get('FFC_REFERENCE_ROOT') or _default_root()
 
 
 def available() -> bool:

@@ -73,10 +73,67 @@ def main():
                 err = float((got.double().cpu() - want).norm() / want.norm())
                 assert err <= tol, (precision, s, err)
         del head
+    sharded_checkpoint_resume(rank, world, dev)
+    long_run_odd_queue(rank, world, dev)
     dist.barrier()
     if rank == 0:
         print('DIST_GPU_OK', world)
     dist.destroy_process_group()
+
+
+def sharded_checkpoint_resume(rank, world, dev):
+    """ShardedFFCHead.checkpoint() / load_checkpoint() over NCCL: a head resumed from the per-rank snapshot continues bit-identically."""
+    import io
+    from ffc_b200.dist import ShardedFFCHead
+    D, Q, B, N = 128, 4096, 64, 6000
+    gen = torch.Generator().manual_seed(40 + rank)
+
+    def batch():
+        xl = torch.randint(0, N, (B,), generator=gen)
+        yl = torch.cat([xl[:B // 2], torch.randint(0, N, (B - B // 2,), generator=gen)])
+        return F.normalize(torch.randn(B, D, generator=gen)).to(dev), F.normalize(torch.randn(B, D, generator=gen)).to(dev), xl, yl
+    torch.manual_seed(1)
+    a = ShardedFFCHead(D, Q, 32.0, 'Arc', 0.5, max_batch=B, device=dev)
+    for _ in range(4):
+        a.forward_pair(*batch())
+    buf = io.BytesIO()
+    torch.save(a.checkpoint(), buf)
+    buf.seek(0)
+    b = ShardedFFCHead(D, Q, 32.0, 'Arc', 0.5, max_batch=B, device=dev)
+    b.load_checkpoint(torch.load(buf, weights_only=False))
+    for _ in range(3):
+        bt = batch()
+        for u, v in zip(a.forward_pair(*bt), b.forward_pair(*bt)):
+            assert torch.equal(u, v)
+        assert a.backend.lru.state_dict() == b.backend.lru.state_dict() and torch.equal(a.backend.queue, b.backend.queue)
+
+
+def long_run_odd_queue(rank, world, dev):
+    """A queue size that is not a power of two and R*B >= 4096 keys per pass (several chunks of the LRU's resolve CTA in one call, ring
+    space reserved per pass): 40 steps with evictions; every rank's LRU stays equal to the oracle's LRU(Q/R) fed the keys it owns."""
+    from ffc_b200.dist import ShardedFFCHead
+    from oracle.lru_ref import LRU as RefLRU
+    D, B = 64, 4096 // world
+    Q = 1000 * world
+    N = 5 * Q
+    torch.manual_seed(2)
+    head = ShardedFFCHead(D, Q, 32.0, 'AM', 0.4, max_batch=B, device=dev)
+    ref = RefLRU(Q // world)
+    gen = torch.Generator().manual_seed(9)
+    for s in range(40):
+        n = world * B
+        xl = torch.randint(0, N, (n,), generator=gen)
+        yl = torch.randint(0, N, (n,), generator=gen)
+        x = F.normalize(torch.randn(n, D, generator=gen))
+        y = F.normalize(torch.randn(n, D, generator=gen))
+        sl = slice(rank * B, (rank + 1) * B)
+        loss, _, _ = head.forward_pair(x[sl].to(dev), y[sl].to(dev), xl[sl], yl[sl])
+        for k in xl.tolist():                       # the commit pass's gallery keys, global batch order; the rollback pass undoes itself
+            if k % world == rank:
+                ref.get(k)
+        if s % 8 == 7:
+            assert head.backend.lru.state_dict() == ref.state_dict(), ('odd queue', s)
+            assert bool(torch.isfinite(loss))
 
 
 if __name__ == '__main__':

@@ -44,16 +44,22 @@ def test_config_object_is_shared_by_both_arms():
 
 
 def test_reference_arm_json_line():
-    env = dict(os.environ, OMP_NUM_THREADS='4')
+    env = dict(os.environ, OMP_NUM_THREADS='1')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'c2', '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['metric'] == 'ffc_head_fwd_bwd_samples_per_s' and line['unit'] == 'samples/s'
     assert line['higher_is_better'] is True and line['value'] > 0 and line['vs_baseline'] is None
-    assert line['config'] == _bench().config_of(_bench().WORKLOADS['c2'], 1)
+    # the shared keys are our arm's config; the reference arm adds the shape it really ran and says that the figure is extrapolated
+    ours = _bench().config_of(_bench().WORKLOADS['c2'], 1)
+    assert {k: line['config'][k] for k in ours} == ours
+    rs = line['config']['reference_sample']
+    assert rs['rows_per_pass'] == 512 and rs['queue'] == 32768 and rs['extrapolated'] is True
     cb = line['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == line['value'] and 'queue' in cb['sample']
+    from oracle import ref_shim
+    assert cb['kind'] == ('reference' if ref_shim.available() else 'port') and cb['value'] == line['value'] and 'queue' in cb['sample']
+    assert cb['cores'] >= min(4, os.cpu_count())          # all host threads, whatever OMP_NUM_THREADS says (torchrun exports 1)
     assert line['e2e'] == {'value': line['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     # a non-zero rank of a torchrun launch exits 0 without work
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],

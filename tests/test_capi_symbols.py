@@ -130,7 +130,7 @@ def test_head_create_rejects_unsupported_widths_up_front():
     for D, prec, frag in ((192, 0, b'64, 128, 256 or 512'), (130, 1, b'multiple of 4'), (1024, 1, b'<= 512')):
         cfg = _capi.HeadConfig(64, 1024, 1024, 0, D, 0, 32.0, 0.4, 3, prec)
         assert lib.ffc_head_create(C.byref(cfg), C.byref(h)) == 1 and frag in lib.ffc_last_error(), (D, lib.ffc_last_error())
-    cfg = _capi.HeadConfig(64, 1024, 1024, 0, 128, 0, 64.0, 0.4, 3, 0)          # scale + fixed max must stay below 87 (fp32 exp range)
+    cfg = _capi.HeadConfig(64, 1024, 1024, 0, 128, 0, 80.0, 0.4, 3, 0)          # logit range 2 * scale must fit the fp32 exponent range (<= 154): s <= 77
     assert lib.ffc_head_create(C.byref(cfg), C.byref(h)) == 1 and b'scale' in lib.ffc_last_error()
     cfg = _capi.HeadConfig(64, 1024, 1024, 0, 128, 0, 32.0, 0.4, 11, 0)          # ffc.py:48: hard_neg <= 10
     assert lib.ffc_head_create(C.byref(cfg), C.byref(h)) == 1 and b'topk' in lib.ffc_last_error()

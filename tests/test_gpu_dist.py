@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('world', [2])
+@pytest.mark.parametrize('world', [2, 8])
 def test_sharded_head_nccl(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')

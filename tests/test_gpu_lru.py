@@ -161,3 +161,53 @@ def test_export_import_round_trip():
     b.clear()
     assert b.state_dict() == [] and b.cur_idx == 0
     assert b.get(77) == 0
+
+
+@pytest.mark.parametrize('cap,pass_keys', [(7409, 8192), (1024, 4096), (100, 3000)])
+def test_long_run_multi_chunk_passes(cap, pass_keys):
+    """A sharded head's pattern (ffc_b200/dist.py): every pass brings R*B keys -- several 1024-key chunks of the resolve CTA -- as ONE
+    ffc_lru_assign call, journaled passes are undone, commit passes stay; capacities that are not powers of two (the reference's
+    default queue_size is 7409, ffc.py:11).  Ring space for the whole pass is reserved before its first chunk: 60 steps never hit
+    'recency ring full', and the state matches the oracle after every pass."""
+    dev = torch.device('cuda')
+    rng = random.Random(cap + pass_keys)
+    lru, ref = _dev_lru(cap), RefLRU(cap)
+    qpos = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    ref_qpos = [0] * cap
+    universe = 6 * cap
+    for step in range(60):
+        for journal in (True, False):
+            keys = [rng.randrange(universe) for _ in range(pass_keys)]
+            kt = torch.tensor(keys, dtype=torch.int64, device=dev)
+            rows = torch.empty(pass_keys, dtype=torch.int32, device=dev)
+            cols = torch.empty(pass_keys, dtype=torch.int32, device=dev)
+            q_before = list(ref_qpos)
+            lru.assign(kt, journal=journal, qpos=qpos, rows=rows, cols=cols)
+            r_rows, r_cols, _, _ = _ref_batch(ref, ref_qpos, keys, journal)
+            assert cols.tolist() == r_cols and rows.tolist() == r_rows, (step, journal)
+            if journal:
+                lru.undo(-1, qpos)
+                ref.rollback_steps(pass_keys)
+                ref_qpos[:] = q_before
+                assert lru.journal_len == 0
+        if step % 10 == 9:
+            assert lru.state_dict() == ref.state_dict() and qpos.cpu().tolist() == ref_qpos
+    assert lru.state_dict() == ref.state_dict() and lru.cur_idx == ref.cur_idx
+
+
+def test_device_side_key_count_stops_the_chunk_walk():
+    """n_dev (a rank's share of an all-gathered batch, known only on the device): keys [0, *n_dev) are processed -- across chunk
+    boundaries -- and the outputs of the remaining positions stay untouched."""
+    dev = torch.device('cuda')
+    rng = random.Random(77)
+    cap, n = 3000, 8192
+    lru, ref = _dev_lru(cap), RefLRU(cap)
+    for n_eff in (1100, 0, 1024, 2500, 8192, 1):
+        keys = [rng.randrange(5 * cap) for _ in range(n)]
+        kt = torch.tensor(keys, dtype=torch.int64, device=dev)
+        cols = torch.full((n,), -7, dtype=torch.int32, device=dev)
+        nd = torch.tensor([n_eff], dtype=torch.int32, device=dev)
+        lru.assign(kt, cols=cols, n_dev=nd)
+        got = cols.tolist()
+        assert got[:n_eff] == [ref.get(k) for k in keys[:n_eff]] and all(v == -7 for v in got[n_eff:])
+        assert lru.state_dict() == ref.state_dict()

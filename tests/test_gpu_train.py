@@ -1,0 +1,146 @@
+"""SURVEY.md 8(f) rank 4 on a GPU: the training-step harness (ffc_b200/train.py, main.py:23-86) around ``ffc_b200.FFC``
+
+  * with a toy backbone ending in ``FFCTail`` (BatchNorm1d + L2 normalise kernels): 12 steps, label hand-over one step ahead
+    (``prefetch_labels``), snapshots in the reference's wire format, resume;
+  * with the REFERENCE's own backbones (model/mobilefacenet_def.py, model/resnet_arcface.py from the staged reference tree
+    oracle/_ref, see oracle/make_ref.py) at the C1 / C2 model configurations: ``ffc_b200.FFC`` as the drop-in for the reference's
+    ``FFC`` module under main.py:64-69's call -- same weights, same queue, same batches, the reference module running its own eager
+    CUDA path (fp16 autocast) next to ours: LRU / queue positions bit-exact step by step, loss and parameter gradients within the
+    bf16 tolerance.
+"""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference' if os.path.isfile('/root/reference/ffc.py') else os.path.join(ROOT, 'oracle', '_ref')
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, 'model', '__init__.py')),
+                               reason='reference backbones not staged (run __graft_entry__.build() where /root/reference exists)')
+
+
+def test_train_loop_toy_backbone_with_tail_and_prefetch():
+    import ffc_b200
+    from ffc_b200 import train as T
+    dev = torch.device('cuda')
+    D, Q, B, S = 64, 512, 32, 8
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(3 * S * S, D)
+            self.features = ffc_b200.FFCTail(D)
+
+        def forward(self, x):
+            return self.features(self.fc(torch.flatten(x, 1)).float())
+
+    def make():
+        torch.manual_seed(0)
+        return ffc_b200.FFC('x', D, queue_size=Q, loss_type='AM', margin=0.4, probe_net=Net(), gallery_net=Net(), max_batch=B).to(dev)
+    net = make()
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.05, momentum=0.9)
+    scaler = torch.amp.GradScaler('cuda')
+    src = T.SyntheticSource(num_class=300, batch_size=B, image_size=S, batches_per_epoch=12, seed=2)
+    logs = []
+    with tempfile.TemporaryDirectory() as d:
+        n = T.train_one_epoch(src.id_loader(), src.instance_loader(), net, opt, scaler, saved_dir=d, save_every=4, device=dev, log=logs.append)
+        assert n == 12 and sorted(os.listdir(d)) == ['1.pt', '2.pt', '3.pt'], os.listdir(d)
+        ck = torch.load(os.path.join(d, '3.pt'), weights_only=False)
+    assert all(np.isfinite(l['loss']) for l in logs), logs
+    assert net.prefetch_hits == 11                       # every step but the first ran on bookkeeping handed over one step ahead
+    assert len(ck['lru']) == net.lru.cur_idx > 0 and tuple(ck['fc'].shape) == (2, Q, D) and set(ck) == {'state_dict', 'lru', 'fc', 'qp'}
+    net2 = make()
+    net2.load_checkpoint(ck)
+    assert net2.lru.state_dict() == net.lru.state_dict() and torch.equal(net2.queue, net.queue)
+    assert net2.queue_position_dict == net.queue_position_dict
+    # the prefetched path is the plain path: the same 12 steps without handing labels over give the same losses, bit for bit
+    net3 = make()
+    opt3 = torch.optim.SGD([p for p in net3.parameters() if p.requires_grad], lr=0.05, momentum=0.9)
+    sc3 = torch.amp.GradScaler('cuda')
+    net3.prefetch_labels = None                          # train_one_epoch then skips the hand-over
+    logs3 = []
+    T.train_one_epoch(src.id_loader(), src.instance_loader(), net3, opt3, sc3, save_every=4, device=dev, log=logs3.append)
+    assert [l['loss'] for l in logs3] == [l['loss'] for l in logs] and net3.prefetch_hits == 0
+    assert net3.lru.state_dict() == net.lru.state_dict() and torch.equal(net3.queue, net.queue)
+
+
+def _distinct_labels(gen, n_ids, B):
+    """x / y labels of one batch, main.py:53-60 composition, without a repeated label inside either side: the reference's CUDA
+    `queue[r, c] = g` with a repeated (r, c) is undefined, so the drop-in comparison avoids the case"""
+    h = B // 2
+    perm = torch.randperm(n_ids, generator=gen)
+    ids, a, b = perm[:h], perm[h:B], perm[B:B + h]
+    return torch.cat([ids, a]), torch.cat([ids, b])
+
+
+@needs_ref
+@pytest.mark.parametrize('net_type,D,B,Q,steps', [('mobile', 128, 64, 4096, 3), ('ir50', 512, 16, 1024, 3)])
+def test_drop_in_for_the_reference_module_with_its_own_backbones(net_type, D, B, Q, steps):
+    """C1's model (MobileFaceNet, batch 64, 10k identities, queue 4096, 112x112) and C2's backbone (iresnet50; small batch / queue to
+    keep the test short).  Identities are drawn from a pool of 3 x batch so that hits, `ones`, misses and outliers all occur."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import ffc as ref_ffc                                  # the unmodified reference module (oracle/_ref or /root/reference)
+    import ffc_b200
+    assert os.path.realpath(ref_ffc.__file__).startswith(os.path.realpath(REF))
+    dev = torch.device('cuda')
+    torch.manual_seed(1)
+    ref = ref_ffc.FFC(net_type, D, queue_size=Q, scale=32.0, loss_type='Arc', margin=0.5).to(dev)
+    ours = ffc_b200.FFC(net_type, D, queue_size=Q, scale=32.0, loss_type='Arc', margin=0.5, max_batch=B)
+    ours.probe_net.load_state_dict(ref.probe_net.state_dict())
+    ours.gallery_net.load_state_dict(ref.gallery_net.state_dict())
+    ours.queue.copy_(ref.queue.detach().cpu())
+    ours = ours.to(dev)
+    ref.train(), ours.train()
+    gen = torch.Generator().manual_seed(2)
+    pool = 3 * B                                           # identities recur across steps: targets are resident from step 2 on
+    seen_pos = 0
+    for s in range(steps):
+        xl, yl = _distinct_labels(gen, pool, B)
+        x = torch.randn(B, 3, 112, 112, generator=gen).to(dev)
+        y = torch.randn(B, 3, 112, 112, generator=gen).to(dev)
+        out = []
+        for m in (ref, ours):
+            m.zero_grad(set_to_none=True)
+            with contextlib.redirect_stdout(io.StringIO()), torch.amp.autocast('cuda'):          # main.py:64-65
+                loss = m(x, y, xl, yl)
+            (loss * 1024.0).backward()                                                            # main.py:69 (a GradScaler's factor)
+            last = [p for p in m.probe_net.parameters() if p.grad is not None][-1]
+            out.append((float(loss), last.grad.detach().float().clone(), sum(float(p.grad.float().pow(2).sum()) for p in m.probe_net.parameters() if p.grad is not None) ** 0.5))
+        (lr, gr, nr), (lo, go, no) = out
+        assert ours.lru.state_dict() == ref.lru.state_dict(), s
+        assert ours.queue_position_dict == ref.queue_position_dict, s
+        assert torch.allclose(ours.queue, ref.queue, rtol=0, atol=1e-3), s     # enqueue is a copy of the gallery embeddings (two module instances: conv algorithms may differ in the last bits)
+        assert abs(lo - lr) <= 1e-2 * abs(lr), (s, lo, lr)
+        assert float((go - gr).norm() / (gr.norm() + 1e-30)) <= 5e-2, (s, float((go - gr).norm() / gr.norm()))
+        assert abs(no - nr) <= 5e-2 * nr, (s, no, nr)
+        seen_pos += sum(1 for v in ours.last_bookkeeping()[2] if v >= 0)
+    assert seen_pos > 0
+
+
+@needs_ref
+def test_train_one_epoch_with_the_reference_mobilefacenet():
+    """C1 as main.py runs it (MobileFaceNet feat_dim 128, batch 64, queue 4096, 10k identities, SGD, AMP GradScaler): the loop runs on
+    the device with label hand-over, the loss is finite and falls on a learnable synthetic source."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import ffc_b200
+    from ffc_b200 import train as T
+    dev = torch.device('cuda')
+    torch.manual_seed(0)
+    net = ffc_b200.FFC('mobile', 128, queue_size=4096, scale=32.0, loss_type='Arc', margin=0.5, max_batch=64).to(dev)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.05, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    scaler = torch.amp.GradScaler('cuda')
+    src = T.SyntheticSource(num_class=10000, batch_size=64, image_size=112, batches_per_epoch=8, seed=3)
+    logs = []
+    n = T.train_one_epoch(src.id_loader(), src.instance_loader(), net, opt, scaler, save_every=2, device=dev, log=logs.append)
+    assert n == 8 and len(logs) == 4 and all(np.isfinite(l['loss']) for l in logs), logs
+    assert net.prefetch_hits == 7 and net.lru.cur_idx > 64

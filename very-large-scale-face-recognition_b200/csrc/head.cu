@@ -867,7 +867,15 @@ __global__ void head_p_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
 }
 
-static float fixed_max_of(const ffc_head_config& c) { return c.loss_type == FFC_LOSS_SV ? c.scale * (2.f * SV_T - 1.f) : c.scale; }
+// The softmax reference point M.  The logits are bounded by construction (unit-norm rows: |cos| <= 1), z in [z_min, z_max] with
+// z_max = scale (SV: scale * (2t - 1), ffc.py:124), z_min = -scale, so a FIXED reference is exact as long as every e^(z - M) and
+// their sum over the queue stay normal fp32 numbers: M >= z_max - 67 (2^30 columns of e^67 < 2^127) and M <= z_min + 87.  M is the
+// midpoint of that window, (z_max + z_min + 20) / 2 -- 10 for AM / Arc at ANY scale, e.g. the customary ArcFace s = 64: nothing is
+// flushed, nothing overflows, no rescaling of the accumulators is ever needed.  (M = scale, the usual "subtract the largest
+// possible logit", would push e^(z_min - M) = e^(-2 scale) below the normal range for scale >= 43.5.)
+static float logit_max_of(const ffc_head_config& c) { return c.loss_type == FFC_LOSS_SV ? c.scale * (2.f * SV_T - 1.f) : c.scale; }
+static float fixed_max_of(const ffc_head_config& c) { return 0.5f * (logit_max_of(c) - c.scale + 20.f); }
+static bool fixed_max_ok(const ffc_head_config& c) { return c.scale > 0.f && logit_max_of(c) + c.scale <= 154.f; }
 
 }  // namespace ffc
 
@@ -896,9 +904,9 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
     FFC_REQUIRE(cfg->feat_dim == 64 || cfg->feat_dim == 128 || cfg->feat_dim == 256 || cfg->feat_dim == 512,
                 "ffc_head_create: the bf16 tensor-core path is built for feat_dim 64, 128, 256 or 512 (got %d); other widths: FFC_PREC_FP32",
                 cfg->feat_dim);
-    // exp(s*z - M) must stay a normal float: range 2*M
-    FFC_REQUIRE(cfg->scale + fixed_max_of(*cfg) < 87.f, "ffc_head_create: scale %.1f too large for the fixed-max softmax (scale + M must be < 87)", cfg->scale);
   }
+  FFC_REQUIRE(fixed_max_ok(*cfg), "ffc_head_create: scale %.1f outside (0, %.1f]: the logit range must fit the fp32 exponent range around the fixed softmax reference",
+              cfg->scale, cfg->loss_type == FFC_LOSS_SV ? 154.f / (2.f * SV_T) : 77.f);
   ffc_head* h = new ffc_head();
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;

@@ -209,7 +209,7 @@ struct ResolveArgs {
   JournalEntry* journal;
   int64_t jcap;
   const int64_t* keys;
-  const int32_t* s0;
+  int32_t* s0;          // [NB] table lookups of the current chunk (chunk 0: lru_lookup_kernel; later chunks: the CTA itself)
   int n;
   const int32_t* n_dev;   // optional device-side key count (sharded callers): n_eff = clamp(*n_dev - n_base, 0, n)
   int n_base;
@@ -397,19 +397,10 @@ __device__ void run_sim(ResolveSmem& S, const ResolveArgs& a, int64_t head, int 
   S.sim_done = (i >= a.n);
 }
 
-__global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_in) {
-  ResolveArgs a = a_in;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ResolveSmem& S = *reinterpret_cast<ResolveSmem*>(smem_raw);
+// One chunk (<= NB keys) of a batch, all threads of the single resolve CTA.  Returns false when the device error flag was raised.
+__device__ bool resolve_chunk(const ResolveArgs& a, ResolveSmem& S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int n_eff = a.n;
-  if (a.n_dev) {
-    n_eff = *a.n_dev - a.n_base;
-    n_eff = n_eff < 0 ? 0 : (n_eff > a.n ? a.n : n_eff);
-  }
-  const int n = n_eff;
-  if (n == 0) return;
-  a.n = n;
+  const int n = a.n;
   LruState* st = a.st;
   const int cur0 = st->cur_idx;
   const int64_t head = st->head, tail = st->tail, jlen = st->jlen;
@@ -417,7 +408,7 @@ __global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_
   // ring / journal capacity guards (host keeps conservative counters; this is the backstop)
   if (head + n - tail > a.rmask + 1 || (a.do_journal && jlen + n > a.jcap)) {
     if (tid == 0) st->err = (head + n - tail > a.rmask + 1) ? 1 : 2;
-    return;
+    return false;
   }
 
   for (int c = tid; c < LHSZ; c += NT) {
@@ -571,7 +562,7 @@ __global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_
   }
   if (S.err) {
     if (tid == 0) st->err = S.err;
-    return;
+    return false;
   }
 
   // R4: outputs
@@ -659,6 +650,39 @@ __global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_
       for (int j = 0; j < len; ++j) rank += S.lh[j] < mine ? 1 : 0;     // slots are distinct
       a.ones_list[n0 + rank] = mine;
     }
+  }
+  return true;
+}
+
+// ONE launch per batch of any size: the CTA walks the batch in chunks of NB keys (the reference semantics are sequential, so
+// chunks cannot run side by side).  The table lookups of chunk 0 come from lru_lookup_kernel (many CTAs, launched just before);
+// later chunks depend on the inserts / evictions of the earlier ones, so the CTA looks their keys up itself (one warp per key).
+// With a device-side key count (sharded callers) the walk stops at clamp(*n_dev - n_base, 0, n): no empty launches.
+__global__ void __launch_bounds__(NT, 1) lru_resolve_kernel(const ResolveArgs a_in) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ResolveSmem& S = *reinterpret_cast<ResolveSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int n_total = a_in.n;
+  if (a_in.n_dev) {
+    n_total = *a_in.n_dev - a_in.n_base;
+    n_total = n_total < 0 ? 0 : (n_total > a_in.n ? a_in.n : n_total);
+  }
+  for (int base = 0; base < n_total; base += NB) {
+    ResolveArgs a = a_in;
+    a.n = n_total - base < NB ? n_total - base : NB;
+    a.keys += base;
+    a.cols_out += base;
+    if (a.rows_out) a.rows_out += base;
+    if (a.hit_out) a.hit_out += base;
+    if (base > 0) {
+      __syncthreads();      // the previous chunk's table / state updates are complete
+      for (int t = warp; t < a.n; t += NT / 32) {
+        const int32_t s = ht_find_warp(a.ht_key, a.ht_slot, a.nwin, a.keys[t], lane, nullptr);
+        if (lane == 0) a.s0[t] = s;
+      }
+      __syncthreads();
+    }
+    if (!resolve_chunk(a, S)) return;
   }
 }
 
@@ -885,8 +909,10 @@ extern "C" int ffc_lru_create(int64_t capacity, int64_t journal_capacity, ffc_lr
   ffc_lru* h = new ffc_lru();
   memset(h, 0, sizeof(*h));
   h->cap = capacity;
-  h->T = std::max<int64_t>(next_pow2(4 * capacity), 16384);
-  h->RC = std::max<int64_t>(next_pow2(4 * capacity), 16384);
+  // 4x the capacity, and never less than 2^18: one pass may bring FFC_LRU_MAX_KEYS accesses (plus as many journaled ones
+  // outstanding) on top of `capacity` live records, whatever the capacity
+  h->T = std::max<int64_t>(next_pow2(4 * capacity), (int64_t)1 << 18);
+  h->RC = std::max<int64_t>(next_pow2(4 * capacity), (int64_t)1 << 18);
   h->jcap = journal_capacity > 0 ? journal_capacity : 65536;
   h->n_blk = ceil_div64(h->RC, 1024);
   FFC_CUDA(cudaMalloc(&h->ht_key, h->T * sizeof(int64_t)));
@@ -940,14 +966,19 @@ extern "C" int ffc_lru_clear(ffc_lru_t* h, void* stream) {
   return FFC_OK;
 }
 
+// Make room for `reserve` more accesses (the WHOLE batch about to be resolved, not one chunk of it: once its first journaled
+// chunk is outstanding nothing can be compacted any more).
+static int lru_maintain_for(ffc_lru_t* h, int64_t reserve, cudaStream_t s) {
+  int rc = FFC_OK;
+  if (h->jlen_host == 0 && h->ring_used_ub + reserve + 2 * NB > h->RC) rc = lru_compact_ring(h, s);
+  if (rc) return rc;
+  if (h->jlen_host == 0 && h->ht_used_ub + 2 * reserve + 2 * NB > h->T / 2) rc = lru_rebuild_ht(h, s);
+  return rc;
+}
+
 extern "C" int ffc_lru_maintain(ffc_lru_t* h, void* stream) {
   FFC_REQUIRE(h != nullptr, "ffc_lru_maintain: NULL handle");
-  cudaStream_t s = (cudaStream_t)stream;
-  int rc = FFC_OK;
-  if (h->jlen_host == 0 && h->ring_used_ub + 2 * NB > h->RC) rc = lru_compact_ring(h, s);
-  if (rc) return rc;
-  if (h->jlen_host == 0 && h->ht_used_ub + 2 * NB > h->T / 2) rc = lru_rebuild_ht(h, s);
-  return rc;
+  return lru_maintain_for(h, 0, (cudaStream_t)stream);
 }
 
 extern "C" int ffc_lru_view(ffc_lru_t* h, const int64_t* keys_dev, int n, int32_t* slots_out, void* stream) {
@@ -963,17 +994,17 @@ extern "C" int ffc_lru_assign(ffc_lru_t* h, const int64_t* keys_dev, int n, int 
                               int32_t* cols_out, uint8_t* hit_out, int32_t* ones_list_dev, int32_t* n_ones_dev, uint32_t* cmask_dev,
                               const int32_t* n_dev, int n_base, void* stream) {
   FFC_REQUIRE(h && keys_dev && cols_out, "ffc_lru_assign: NULL argument");
-  FFC_REQUIRE(n >= 1 && n <= NB, "ffc_lru_assign: n=%d outside [1,%d]", n, NB);
+  FFC_REQUIRE(n >= 1 && n <= FFC_LRU_MAX_KEYS, "ffc_lru_assign: n=%d outside [1,%d]", n, FFC_LRU_MAX_KEYS);
   FFC_REQUIRE(!ones_list_dev || (n_ones_dev && cmask_dev), "ffc_lru_assign: ones_list needs n_ones and cmask");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = ffc_lru_maintain(h, s);
+  int rc = lru_maintain_for(h, n, s);
   if (rc) return rc;
   if (journal) FFC_REQUIRE(h->jlen_host + n <= h->jcap, "ffc_lru_assign: journal capacity %lld exceeded", (long long)h->jcap);
   if (h->ring_used_ub + n > h->RC) {
     set_error("ffc_lru_assign: recency ring full with %lld journaled accesses outstanding; undo or commit first", (long long)h->jlen_host);
     return FFC_ERR_STATE;
   }
-  rc = ffc_lru_view(h, keys_dev, n, h->s0, s);
+  rc = ffc_lru_view(h, keys_dev, std::min(n, NB), h->s0, s);     // chunk 0; the resolve CTA looks later chunks up itself
   if (rc) return rc;
   ResolveArgs a;
   a.ht_key = h->ht_key;
@@ -1017,7 +1048,8 @@ extern "C" int ffc_lru_undo(ffc_lru_t* h, int64_t steps, uint8_t* qpos_dev, void
   lru_undo_kernel<<<1, NT, sizeof(UndoSmem), s>>>(h->ht_key, h->ht_slot, h->T / 32, h->slot_key, h->last_pos, h->st, h->journal, m, qpos_dev);
   FFC_LAUNCH_CHECK();
   h->jlen_host -= m;
-  h->ht_used_ub += m;  // re-inserted old keys may consume never-used cells
+  h->ring_used_ub -= m;  // the undone accesses' ring records are gone (head is rolled back)
+  h->ht_used_ub += m;    // re-inserted old keys may consume never-used cells
   return FFC_OK;
 }
 

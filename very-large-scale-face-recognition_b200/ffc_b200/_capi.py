@@ -9,7 +9,8 @@ LIB_PATH = os.environ.get('FFC_B200_LIB', os.path.join(_HERE, 'libffc_b200.so'))
 
 LOSS_TYPES = {'AM': 0, 'Arc': 1, 'SV': 2}
 PRECISIONS = {'bf16': 0, 'fp32': 1}
-LRU_MAX_BATCH = 1024
+LRU_MAX_BATCH = 1024     # keys per chunk of the resolve CTA
+LRU_MAX_KEYS = 65536     # keys per ffc_lru_assign call
 TOPK_MAX = 10
 KEY_RESERVED = (-(1 << 63), -(1 << 63) + 1)
 

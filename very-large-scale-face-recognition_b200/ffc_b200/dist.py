@@ -370,6 +370,8 @@ class ShardedFFCHead:
             ev.record(self._side)
         self._pre = dict(xl=xl_all, yl=yl_all, ctx=ctx, ev=ev, src=(x_label, y_label))
 
+    prefetch_labels = prefetch          # the name ffc_b200/train.py looks for (same hook on the one-GPU head)
+
     def _gather_labels(self, x_label, y_label, group=None):
         B, R = self.B, self.R
         own = torch.empty(2 * B, dtype=torch.int64, device=self.dev)

@@ -108,6 +108,9 @@ class FFCHead(Module):
         self._compact = {}
         self._pending_lru = None
         self._pending_qpos = None
+        self._mirror_version, self._mirror_ptr = -1, 0
+        self._pre = None                # rollback-pass bookkeeping of the next forward_pair (prefetch_labels)
+        self.prefetch_hits = 0          # forward_pair calls that consumed prefetched bookkeeping
 
     # -- lazy device state ------------------------------------------------------------------------
     def _ensure(self):
@@ -115,8 +118,20 @@ class FFCHead(Module):
         if not q.is_cuda:
             raise _capi.FFCError('the FFC head runs on a CUDA device only: move the module with .cuda() (no CPU fallback)')
         if self._dev == q.device and self._lru is not None:
+            # a torch-level write to `queue` since the mirror was made (module.load_state_dict(), queue.copy_(), ...) bumps the buffer's
+            # version counter; the kernels' own writes go through raw pointers and keep fp32 rows and mirror in step
+            if q._version != self._mirror_version or q.data_ptr() != self._mirror_ptr:
+                self.sync_mirror()
             return
         dev = q.device
+        if self._lru is not None:
+            # the module was moved to another device after use: carry the LRU (order and slots) and the queue positions over, and
+            # release the old device's head
+            self._side.synchronize()
+            self._pending_lru = self._lru.state_dict()
+            self._pending_qpos = self.qpos.cpu()
+            self._lib.ffc_head_destroy(self.__dict__.pop('_h'))
+            self._lru, self._pre = None, None
         self._lib = _capi.lib()
         Q, D, R = self.queue_size, self.feat_dim, self.max_batch
         with torch.cuda.device(dev):
@@ -191,6 +206,7 @@ class FFCHead(Module):
         q = self.queue
         assert q.is_contiguous() and q.dtype == torch.float32
         check(self._lib.ffc_cast_bf16(q.data_ptr(), self.queue_bf16.data_ptr(), q.numel(), torch.cuda.current_stream(q.device).cuda_stream))
+        self._mirror_version, self._mirror_ptr = q._version, q.data_ptr()
 
     # -- reference attribute: ffc.py:41-43 ------------------------------------------------------------
     @property
@@ -283,6 +299,7 @@ class FFCHead(Module):
 
     def _pass(self, p, g, probe_label, gallery_label, commit):
         self._ensure()
+        self._drop_prefetch()
         B = self._check_batch(p, g)
         with torch.cuda.device(self._dev):
             main = torch.cuda.current_stream(self._dev)
@@ -290,6 +307,39 @@ class FFCHead(Module):
                                   self._on_device(probe_label) or self._on_device(gallery_label))
             main.wait_event(done)
             return self._finish(0 if not commit else 1, p, g, B, commit, main)
+
+    def prefetch_labels(self, x_label, y_label):
+        """Hand over the labels of the NEXT :meth:`forward` / :meth:`forward_pair` now (they are CPU tensors the
+        loader has long before the images have gone through the backbones, main.py:59-60).  The rollback pass's LRU bookkeeping
+        (ffc.py:214-235, 242-246, 256-259) is enqueued on the bookkeeping stream at once, behind the previous step's commit bookkeeping
+        and the release of bookkeeping set 0 -- i.e. it runs under the previous step's sweeps and the backbones' kernels.  The next call
+        must pass these same label objects; anything else discards the prefetched work (a rollback pass's bookkeeping undoes itself on
+        the LRU; only set 0's `ones` mask is cleared)."""
+        self._ensure()
+        self._drop_prefetch()
+        B = int(torch.as_tensor(x_label).numel())
+        assert 1 <= B <= self.max_batch and int(torch.as_tensor(y_label).numel()) == B
+        with torch.cuda.device(self._dev):
+            main = torch.cuda.current_stream(self._dev)
+            done = self._bookkeep(0, y_label, x_label, B, False, main, self._on_device(x_label) or self._on_device(y_label))
+        self._pre = (x_label, y_label, B, done)
+
+    def _drop_prefetch(self):
+        pre, self._pre = self._pre, None
+        if pre is not None:
+            with torch.cuda.stream(self._side):
+                self._sets[0]['cmask'].zero_()
+
+    def _take_prefetch(self, x_label, y_label, B):
+        pre = self._pre
+        if pre is None:
+            return None
+        if pre[0] is x_label and pre[1] is y_label and pre[2] == B:
+            self._pre = None
+            self.prefetch_hits += 1
+            return pre[3]
+        self._drop_prefetch()
+        return None
 
     def forward_pair(self, p_rb, g_rb, p_cm, g_cm, x_label, y_label):
         """ffc.py:264-267 with embeddings in and no autograd glue: the rollback pass (probe p_rb with labels x_label, gallery g_rb
@@ -304,7 +354,9 @@ class FFCHead(Module):
         with torch.cuda.device(self._dev):
             main = torch.cuda.current_stream(self._dev)
             on_main = self._on_device(x_label) or self._on_device(y_label)
-            done_rb = self._bookkeep(0, y_label, x_label, B, False, main, on_main)
+            done_rb = self._take_prefetch(x_label, y_label, B)
+            if done_rb is None:
+                done_rb = self._bookkeep(0, y_label, x_label, B, False, main, on_main)
             done_cm = self._bookkeep(1, x_label, y_label, B, True, main, False)
             main.wait_event(done_rb)
             l2, d_rb = self._finish(0, p_rb, g_rb, B, False, main)

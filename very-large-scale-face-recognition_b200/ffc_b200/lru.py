@@ -48,8 +48,8 @@ class LRU:
         if cols is None:
             cols = torch.empty(n, dtype=torch.int32, device=self.device)
         s = self._s()
-        for a in range(0, n, _capi.LRU_MAX_BATCH):
-            m = min(_capi.LRU_MAX_BATCH, n - a)
+        for a in range(0, n, _capi.LRU_MAX_KEYS):       # one launch pair per call, whatever the batch size
+            m = min(_capi.LRU_MAX_KEYS, n - a)
             off = lambda t, sz: None if t is None else t.data_ptr() + a * sz
             check(self._lib.ffc_lru_assign(self._h, keys.data_ptr() + a * 8, m, 1 if journal else 0, ptr(qpos), off(rows, 4), off(cols, 4),
                                            off(hit, 1), ptr(ones_list), ptr(n_ones), ptr(cmask), ptr(n_dev), a, s))

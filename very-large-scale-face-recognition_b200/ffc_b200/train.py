@@ -6,7 +6,8 @@ y_label)``.  What it adds over main.py is ordering: the labels of a step are spl
 head has one -- the sharded head, ffc_b200/dist.py) before the images go through the backbones, so the label exchange and the LRU
 bookkeeping run under the previous step's sweeps and the backbones' kernels.
 
-STATUS: host logic covered by tests/test_train_host.py on CPU with a stand-in module; the loop has not been run on a GPU yet.
+Host logic: tests/test_train_host.py (CPU, stand-in module).  On a GPU: tests/test_gpu_train.py (a toy backbone ending in FFCTail, and
+the reference's own MobileFaceNet / iresnet50 from the staged reference tree, C1 / C2 shapes).
 """
 from __future__ import annotations
 
@@ -60,9 +61,10 @@ class SyntheticSource:
         return self.n
 
 
-def train_step(ffc_net, optimizer, scaler, x, y, x_label, y_label, autocast_dtype=torch.bfloat16, device_type='cuda'):
+def train_step(ffc_net, optimizer, scaler, x, y, x_label, y_label, autocast_dtype=None, device_type='cuda'):
     """main.py:53-71: zero_grad, forward under autocast, scaled backward, optimiser step, scaler update.  Returns the loss tensor (not
-    synchronised: main.py reads it only every 1000 iterations)."""
+    synchronised: main.py reads it only every 1000 iterations).  ``autocast_dtype=None`` is main.py:64's ``torch.amp.autocast('cuda')``: the
+    device's default autocast type (fp16 on CUDA, hence the GradScaler)."""
     optimizer.zero_grad()
     with torch.amp.autocast(device_type, dtype=autocast_dtype):
         loss = ffc_net(x, y, x_label, y_label)
@@ -73,10 +75,12 @@ def train_step(ffc_net, optimizer, scaler, x, y, x_label, y_label, autocast_dtyp
 
 
 def train_one_epoch(id_loader, instance_loader, ffc_net, optimizer, scaler, cur_epoch=1, saved_dir=None, real_iter=0, save_every=1000,
-                    lr_scheduler=None, db_size=None, device=None, autocast_dtype=torch.bfloat16, log=None):
+                    lr_scheduler=None, db_size=None, device=None, autocast_dtype=None, log=None, rank=None):
     """main.py:23-86.  ``instance_loader`` drives the epoch; ``id_loader`` is restarted when it runs out (main.py:43-47).  Every
     ``save_every`` iterations the reference's snapshot dict is written (main.py:84-85: probe weights, LRU, queue, queue positions).
-    One batch is composed ahead of the step it feeds, so that its labels can be handed to the head early."""
+    One batch is composed ahead of the step it feeds, so that its labels can be handed to the head early (``prefetch_labels``: both
+    ``ffc_b200.FFC`` and ``ShardedFFCHead`` have it).  ``rank``: with a sharded head every rank saves its own shard, as
+    ``<n>.rank<r>.pt`` (ShardedFFCHead.checkpoint is per rank)."""
     device = torch.device('cuda') if device is None else torch.device(device)
     id_iter = iter(id_loader)
     prefetch = getattr(ffc_net, 'prefetch_labels', None)
@@ -116,5 +120,6 @@ def train_one_epoch(id_loader, instance_loader, ffc_net, optimizer, scaler, cur_
             start = time.time()
             if saved_dir is not None:
                 os.makedirs(saved_dir, exist_ok=True)
-                torch.save(ffc_net.checkpoint(), os.path.join(saved_dir, '%d.pt' % (real_iter // save_every)))   # main.py:84-85
+                name = '%d.pt' % (real_iter // save_every) if rank is None else '%d.rank%d.pt' % (real_iter // save_every, rank)
+                torch.save(ffc_net.checkpoint(), os.path.join(saved_dir, name))   # main.py:84-85
     return real_iter
