@@ -407,7 +407,6 @@ def run_ours(args, w):
     # ---- end to end through the public API from pinned host buffers (e2e) ----
     # fresh batches (other embeddings AND other identities' rows than the ones just enqueued: a re-fed embedding makes its target
     # cosine exactly 1 -- the Arc clamp regime -- and the loss would not be comparable with the device-timed phase)
-    del pinned
     pinned = [tuple(t.pin_memory() for t in b) for b in make_batches(w, n_b, seed=4321, rank=rank, world=world)]
     phase_ms = head.phase_times() if getattr(head, '_timing', None) else None
     if phase_ms is not None:

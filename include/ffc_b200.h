@@ -124,6 +124,21 @@ int ffc_queue_scatter_indexed(float* queue_f32_dev, void* queue_bf16_dev, const 
  * keys_out / order_out [n] (order_out[j] = source position), n_mine_out device scalar. */
 int ffc_route_keys(const int64_t* keys_dev, int n, int n_ranks, int rank, int64_t* keys_out_dev,
                    int32_t* order_out_dev, int32_t* n_mine_out_dev, void* stream);
+/* as ffc_queue_scatter_indexed, and every winning write also records in overlay_map_dev (int32 [2, Q], -1 = no entry; NULL = off)
+ * where the content this (row, slot) had during the CURRENT pass's sweep stays available once later kernels have rewritten the row:
+ *   overlay_table 0 (a rollback pass's enqueue): map = src_row[i]          -- the row is g[src_row[i]] until ffc_queue_restore
+ *   overlay_table 1 (the commit pass that follows): map = 2^30 | i          -- undo[i] keeps what was there before; entries a table-0
+ *                                                                             mark already holds are left alone (needs undo_f32_dev)
+ * ffc_head_finalize_gathered_ex reads through the map; ffc_overlay_clear resets the entries of a pass's (rows, cols) list. */
+int ffc_queue_scatter_overlay(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
+                              const int32_t* cols_dev, const float* g_dev, const int32_t* src_row_dev, int B,
+                              int64_t Q, int D, float* undo_f32_dev, int32_t* overlay_map_dev, int overlay_table,
+                              void* stream);
+int ffc_overlay_clear(int32_t* overlay_map_dev, const int32_t* rows_dev, const int32_t* cols_dev, int n, int64_t Q,
+                      void* stream);
+/* out[e] = slabs[e] + slabs[slab_stride + e] + ... (n_slabs terms, in that order), e < n: the local half of the reduce-scatter
+ * that ffc_head_finalize_gathered_ex starts with its peer stores.  n and slab_stride multiples of 4. */
+int ffc_sum_slabs(const float* slabs_dev, int n_slabs, int64_t slab_stride, int64_t n, float* out_dev, void* stream);
 int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
                       const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
                       void* stream);
@@ -278,6 +293,25 @@ int ffc_head_record_words(const ffc_head_config* cfg, int n_rows, int64_t* words
 int ffc_head_sweep_record(ffc_head_t* h, const ffc_head_pass* in, void* record_out, void* stream);
 int ffc_head_finalize_gathered(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks,
                                int64_t record_stride_words, float* loss_out, float* dp_out, void* stream);
+
+/* ffc_head_finalize_gathered with the two extensions of the sharded head's merged step (ONE exchange point per FFC.forward):
+ *   overlay_*: the finalize of a pass whose queue rows have been rewritten since its sweep (restore, the next pass's enqueue) reads
+ *     those rows where their sweep-time content still is (see ffc_queue_scatter_overlay); NULL map = read the queue.
+ *   dp_peer: device array of n_ranks pointers to the ranks' peer-mapped staging buffers.  Row i of this rank's partial dLoss/dp is
+ *     stored to dp_peer[i / dp_rows_per_rank] + dp_slot_offset + (i % dp_rows_per_rank) * D -- straight into the owner rank's memory
+ *     over NVLink, from the kernel that computes it -- instead of dp_out (which may then be NULL); after a barrier across the ranks
+ *     the owner adds the n_ranks slabs with ffc_sum_slabs.  This is the reduce-scatter of dLoss/dp folded into finalize. */
+typedef struct ffc_head_finalize_opts {
+  const int32_t* overlay_map;
+  const float* overlay_g;      /* table 0 rows: the gathered gallery embeddings of the pass, [.., D] fp32 */
+  const float* overlay_undo;   /* table 1 rows: the undo buffer of the enqueue that followed, [.., D] fp32 */
+  float* const* dp_peer;
+  int32_t dp_rows_per_rank;
+  int64_t dp_slot_offset;      /* in floats */
+} ffc_head_finalize_opts;
+int ffc_head_finalize_gathered_ex(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks,
+                                  int64_t record_stride_words, const ffc_head_finalize_opts* opts, float* loss_out,
+                                  float* dp_out, void* stream);
 
 /* sizes in bytes of the five stats arrays for n rows (one rank's worth) */
 int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]);

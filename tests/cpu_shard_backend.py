@@ -236,3 +236,93 @@ class CpuShardBackend:
         self.lru.ref.restore([(int(k), int(v)) for k, v in st['lru']])
         self.queue = st['queue'].double().clone()
         self.qpos = [int(v) for v in st['qpos']]
+
+
+class _OverlayQueue:
+    """queue[row, loc] with substitutions (the overlay of the merged step: csrc/head.cu FinalizeArgs::ovl_map)"""
+
+    def __init__(self, queue, overlay, counter):
+        self.queue, self.overlay, self.counter = queue, overlay, counter
+
+    def __getitem__(self, idx):
+        key = (int(idx[0]), int(idx[1]))
+        v = self.overlay.get(key)
+        if v is None:
+            return self.queue[key[0], key[1]]
+        self.counter[0] += 1
+        return v
+
+
+class CpuShardBackendM(CpuShardBackend):
+    """The stand-in speaking the record / merged-step protocol of CudaShardBackend (AM / Arc): three bookkeeping sets, one record
+    per pass, finalize from the gathered records, the rollback pass's finalize through an overlay of the rows that restore / the
+    commit enqueue have rewritten.  `use_overlay=False` reads the rewritten queue instead (the test shows that this is wrong)."""
+    record_path = True
+    merged = True
+    _SET_ATTRS = ('rows', 'cols', 'ones', 'saved', 'undo', 'journal', 'written')
+
+    def __init__(self, *a, use_overlay=True, **k):
+        super().__init__(*a, **k)
+        self._sets, self._cur = [dict(), dict(), dict()], 0
+        self._st = {}
+        self.use_overlay = use_overlay
+        self.overlay_reads = 0
+
+    def use_set(self, i):
+        self._sets[self._cur] = {k: self.__dict__.get(k) for k in self._SET_ATTRS}
+        for k in self._SET_ATTRS:
+            self.__dict__[k] = self._sets[i].get(k)
+        self._cur = i
+
+    def _of_set(self, i, name):
+        return self.__dict__.get(name) if i == self._cur else self._sets[i].get(name)
+
+    def scatter(self, g_all, order, save_undo, overlay_table=None):
+        g_compact = g_all[order]
+        last = {}
+        for i, rc in enumerate(zip(self.rows, self.cols)):
+            last[rc] = i
+        self.undo = {rc: self.queue[rc[0], rc[1]].clone() for rc in last}        # previous content (restore; the overlay's table 1)
+        self.written = {rc: g_compact[i].double().clone() for rc, i in last.items()}   # the overlay's table 0
+        for rc, v in self.written.items():
+            self.queue[rc[0], rc[1]] = v
+
+    def overlay_clear(self, set_idx):
+        pass
+
+    def new_records(self, n, n_ranks, passes=1):
+        w = 8 * n + 6 * n * self.k
+        return dict(own=torch.zeros(passes, w, dtype=torch.float64), all=torch.zeros(n_ranks, passes, w, dtype=torch.float64), words=w, passes=passes)
+
+    def sweep_record(self, p_all, label, rec, which=0):
+        n = p_all.shape[0]
+        st = self.new_stats(n, 1)
+        self.sweep(p_all, label, st, 0)
+        self._st[which] = (st, self._cur)
+        rec['own'][which] = torch.cat([st['red'].flatten(), st['topv'][0].flatten(), st['topi'][0].double().flatten()])
+
+    def finalize_gathered(self, p_all, label, rec, n_ranks, which=0, overlay_g=None, route=None):
+        n, k = p_all.shape[0], self.k
+        allr = rec['all'][:, which]                                        # [R, words]
+        own_st, set_idx = self._st[which]
+        st = dict(red=allr[:, :8 * n].sum(0).view(8, n), osum=own_st['osum'],
+                  topv=allr[:, 8 * n:8 * n + 3 * n * k].reshape(n_ranks, 3, n, k),
+                  topi=allr[:, 8 * n + 3 * n * k:].reshape(n_ranks, 3, n, k).to(torch.int32))
+        real = self.queue
+        if overlay_g is not None and self.use_overlay:
+            # rows the commit enqueue (set 1) replaced: their previous content ... unless the rollback enqueue had its own row there
+            overlay = dict(self._of_set(1, 'undo') or {})
+            overlay.update(self._of_set(set_idx, 'written') or {})
+            hits = [0]
+            self.queue = _OverlayQueue(real, overlay, hits)
+        try:
+            # finalize reads the bookkeeping of ITS pass (`ones` positions of the target columns)
+            cur = self._cur
+            self.use_set(set_idx)
+            out = self.finalize(p_all, label, st, n_ranks)
+            self.use_set(cur)
+            return out
+        finally:
+            if self.queue is not real:
+                self.overlay_reads += self.queue.counter[0]
+                self.queue = real

@@ -21,8 +21,12 @@ class ShardedOracle(HeadOracle):
 
     def __init__(self, R, *a, **k):
         super().__init__(*a, **k)
-        self.R, self.Ql = R, self.Q // R
-        self.lrus = [LRU(self.Ql) for _ in range(R)]
+        self.R = R
+        base, rem = divmod(self.Q, R)
+        self.Qls = [base + (1 if r < rem else 0) for r in range(R)]            # ffc_b200/dist.py: the first Q % R shards one slot longer
+        self.offs = [r * base + min(r, rem) for r in range(R)]
+        self.Ql = self.Qls[0]
+        self.lrus = [LRU(ql) for ql in self.Qls]
         self.lru = self
 
     # the subset of the LRU surface HeadOracle uses, routed by identity
@@ -35,17 +39,17 @@ class ShardedOracle(HeadOracle):
 
     def get(self, key):
         r, l = self._route(key)
-        return r * self.Ql + l.get(key)
+        return self.offs[r] + l.get(key)
 
     def try_get(self, key):
         r, l = self._route(key)
         self._log.append(r)
-        return r * self.Ql + l.try_get(key)
+        return self.offs[r] + l.try_get(key)
 
     def view(self, key):
         r, l = self._route(key)
         v = l.view(key)
-        return v if v < 0 else r * self.Ql + v
+        return v if v < 0 else self.offs[r] + v
 
     def rollback_steps(self, n):
         for r in reversed(self._log[-n:]):
@@ -65,10 +69,9 @@ def _worker(rank, world, port, loss_type, ret):
         from cpu_shard_backend import CpuShardBackend
         from ffc_b200.dist import ShardedFFCHead
         torch.manual_seed(0)
-        D, Q, B, n_ids, steps = 16, (64 if world != 3 else 66), 12, 90, 4
+        D, Q, B, n_ids, steps = 16, {2: 64, 3: 67, 4: 70}[world], 12, 90, 4          # 67 / 3 and 70 / 4: uneven shards (the first Q % R one slot longer)
         margin = 0.5 if loss_type == 'Arc' else 0.4
         q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64), dim=2)
-        Ql = Q // world
         head = ShardedFFCHead(D, Q, 32.0, loss_type, margin, max_batch=B,
                               backend_factory=lambda ql, off, n: CpuShardBackend(D, ql, Q, off, n, 32.0, loss_type, margin, hard_neg_k(Q),
                                                                                  queue=q0[:, off:off + ql]))
@@ -227,20 +230,23 @@ def test_sharded_head_label_prefetch_world2_gloo(all_hits):
 
 
 def _worker_merged(rank, world, port, loss_type, ret):
-    """tests/proto_merged_exchange.py: one exchange point per step; results must equal the dense oracle, and must NOT without the overlay"""
+    """The product's merged step (ShardedFFCHead._forward_pair_merged: one statistics exchange per step, the rollback pass's finalize
+    through the overlay) with the stand-in backend: results must equal the dense oracle, and must NOT without the overlay."""
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        from proto_merged_exchange import CpuShardBackend2, MergedShardedHead
+        from cpu_shard_backend import CpuShardBackendM
+        from ffc_b200.dist import ShardedFFCHead
         torch.manual_seed(0)
         # few identities, small queue: in-batch duplicates, evictions, targets and hard negatives inside the rows both passes overwrite
         D, Q, B, n_ids, steps = 16, 32, 12, 40, 6
         margin = 0.5 if loss_type == 'Arc' else 0.4
         q0 = F.normalize(torch.rand(2, Q, D, dtype=torch.float64), dim=2)
-        mk = lambda ov: MergedShardedHead(D, Q, 32.0, loss_type, margin, max_batch=B, use_overlay=ov,
-                                          backend_factory=lambda ql, off, n: CpuShardBackend2(D, ql, Q, off, n, 32.0, loss_type, margin, hard_neg_k(Q),
-                                                                                              queue=q0[:, off:off + ql]))
+        mk = lambda ov: ShardedFFCHead(D, Q, 32.0, loss_type, margin, max_batch=B,
+                                       backend_factory=lambda ql, off, n: CpuShardBackendM(D, ql, Q, off, n, 32.0, loss_type, margin, hard_neg_k(Q),
+                                                                                           queue=q0[:, off:off + ql], use_overlay=ov))
         head, naive = mk(True), mk(False)
+        assert head.merged and naive.merged
         oracle = ShardedOracle(world, D, Q, 32.0, loss_type, margin, queue=q0, dtype=torch.float64)
         gen = torch.Generator().manual_seed(9)
         cen = F.normalize(torch.randn(n_ids, D, generator=gen, dtype=torch.float64))
@@ -251,7 +257,11 @@ def _worker_merged(rank, world, port, loss_type, ret):
             x = F.normalize(cen[xl] + 0.4 * torch.randn(world * B, D, generator=gen, dtype=torch.float64))
             y = F.normalize(cen[yl] + 0.4 * torch.randn(world * B, D, generator=gen, dtype=torch.float64))
             sl = slice(rank * B, (rank + 1) * B)
-            loss, dx, dy = head.forward_pair(x[sl], y[sl], xl[sl], yl[sl])
+            if s % 2:        # labels handed over one step ahead: the rollback bookkeeping lands in the OTHER rollback set (0 / 2 alternate)
+                head.prefetch(xl[sl], yl[sl])
+                loss, dx, dy = head.forward_pair(x[sl], y[sl])
+            else:
+                loss, dx, dy = head.forward_pair(x[sl], y[sl], xl[sl], yl[sl])
             _, dx_n, dy_n = naive.forward_pair(x[sl], y[sl], xl[sl], yl[sl])
             xo, yo = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
             ref = oracle.forward(xo, yo, xl.tolist(), yl.tolist())
@@ -260,18 +270,18 @@ def _worker_merged(rank, world, port, loss_type, ret):
             assert torch.allclose(dx, xo.grad[sl], rtol=1e-8, atol=1e-12), s
             assert torch.allclose(dy, yo.grad[sl], rtol=1e-8, atol=1e-12), s
             assert head.backend.lru.state_dict() == oracle.lrus[rank].state_dict()
-            assert torch.allclose(head.backend.queue, oracle.queue[:, rank * (Q // world):(rank + 1) * (Q // world)].double(), atol=0, rtol=0)
+            assert torch.allclose(head.backend.queue, oracle.queue[:, head.off:head.off + head.Ql].double(), atol=0, rtol=0)
             naive_wrong += int(not torch.allclose(dx_n, xo.grad[sl], rtol=1e-8, atol=1e-12))
-        t = torch.tensor([naive_wrong, head.backend.overlay_reads])
+        t = torch.tensor([naive_wrong, head.backend.overlay_reads, head.prefetch_hits])
         dist.all_reduce(t)
-        assert int(t[0]) > 0 and int(t[1]) > 0, t.tolist()       # the overlay was needed, and it was read
+        assert int(t[0]) > 0 and int(t[1]) > 0 and int(t[2]) == world * (steps // 2), t.tolist()       # the overlay was needed, and it was read
         ret[rank] = 'ok'
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('loss_type', ['Arc', 'SV'])
-def test_merged_exchange_prototype(loss_type):
+@pytest.mark.parametrize('world,loss_type', [(2, 'Arc'), (2, 'AM'), (3, 'Arc')])
+def test_merged_step_one_exchange_gloo(world, loss_type):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     with socket.socket() as s:
@@ -279,8 +289,8 @@ def test_merged_exchange_prototype(loss_type):
         port = s.getsockname()[1]
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker_merged, args=(2, port, loss_type, ret), nprocs=2, join=True)
-    assert dict(ret) == {0: 'ok', 1: 'ok'}
+    mp.spawn(_worker_merged, args=(world, port, loss_type, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: 'ok' for r in range(world)}
 
 
 def _run(world, loss_type):
@@ -302,6 +312,6 @@ def test_sharded_head_world2_gloo(loss_type):
 
 @pytest.mark.parametrize('world,loss_type', [(3, 'Arc'), (4, 'SV')])
 def test_sharded_head_more_ranks_gloo(world, loss_type):
-    """3 ranks (queue 66: shards that are not a power of two) and 4 ranks: candidate sets of several ranks merged per outlier row,
-    target cosines owned by any of them"""
+    """3 ranks (queue 67) and 4 ranks (queue 70) -- queue sizes the rank count does not divide: candidate sets of several ranks merged per
+    outlier row, target cosines owned by any of them"""
     _run(world, loss_type)

@@ -44,7 +44,8 @@ def _run_case(z, precision, tol_loss, tol_grad):
             for val, k in zip(got, ('rows', 'cols', 'labels', 'ones')):
                 assert val == z[f'{pn}_{k}{s}'].tolist(), (s, pn, k)
         assert [list(kv) for kv in m.lru.state_dict()] == z[f'lru{s}'].tolist()
-        assert [m.queue_position_dict[i] for i in range(Q)] == z[f'qpos{s}'].tolist()
+        qp = m.queue_position_dict
+        assert [qp[i] for i in range(Q)] == z[f'qpos{s}'].tolist()
         # numerics: the golden (reference fp32) and the fp64 oracle
         x64 = torch.from_numpy(z[f'x{s}']).double().requires_grad_(True)
         y64 = torch.from_numpy(z[f'y{s}']).double().requires_grad_(True)

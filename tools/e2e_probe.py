@@ -48,3 +48,16 @@ for mode in ('device labels', 'pinned host labels', 'device labels', 'pinned hos
         head.forward_pair(x, y, y, x, xl, yl)
     torch.cuda.synchronize()
     print(f'{mode:22s} free-running: {(time.perf_counter() - t0) * 1e3 / len(bs):.3f} ms/step')
+
+# the regime of round 1's e2e leg: the same batches again, newest first (their x-side identities were committed, the y-side instance
+# identities were not: the rollback pass mixes hits of recent entries with misses)
+bs = [(x.to(dev), y.to(dev), xl.pin_memory(), yl.pin_memory()) for x, y, xl, yl in host][::-1]
+torch.cuda.synchronize()
+for rep in range(2):
+    ts = []
+    for x, y, xl, yl in bs:
+        t0 = time.perf_counter()
+        head.forward_pair(x, y, y, x, xl, yl)
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print(f're-fed batches (newest first), pass {rep}: mean {sum(ts) / len(ts):.3f} ms/step, max {max(ts):.3f}, first five {[round(t, 2) for t in ts[:5]]}')

@@ -540,8 +540,23 @@ struct FinalizeArgs {
   int64_t q_local, col_offset;
   int loss_type;
   float scale, margin, fixed_max;
+  double cos_m, sin_m;         // cos / sin of the margin (Arc), computed once on the host
   float* row_loss;
   float* dp;
+  // Overlay (sharded head with ONE exchange point per step, ffc_b200/dist.py): a queue row that has been rewritten since this pass's
+  // sweep -- restored after a rollback pass, or enqueued by the commit pass that followed -- is read from where its sweep-time
+  // content still is.  ovl_map[row * q_local + slot] = -1, or the source row: bit 30 clear -> ovl_g + idx * D (the gathered gallery
+  // embedding that sat there), bit 30 set -> ovl_undo + idx * D (the previous content a later enqueue saved).  fp32 rows, rounded to
+  // bf16 on the fly exactly as the mirror was.
+  const int32_t* ovl_map;
+  const float* ovl_g;
+  const float* ovl_undo;
+  // Output routing (reduce-scatter folded into finalize): with dp_peer != NULL row i of this rank's partial dLoss/dp is stored to
+  // dp_peer[i / dp_rows_per_rank] + dp_slot_off + (i % dp_rows_per_rank) * D -- the owner rank's peer-mapped staging buffer
+  // (stores travel over NVLink) -- instead of dp[i * D].
+  float* const* dp_peer;
+  int dp_rows_per_rank;
+  int64_t dp_slot_off;
 };
 
 __device__ __forceinline__ float w_elem(const FinalizeArgs& a, int r, int64_t local_slot, int d) {
@@ -551,7 +566,9 @@ __device__ __forceinline__ float w_elem(const FinalizeArgs& a, int r, int64_t lo
 
 // The scalar part of finalize for one row: margin function, log/exp in fp64, top-k merge.  `lsum_at(slot)` returns the row's
 // softmax denominator of stats slot 0..3, `top_at(r, set, q, v, idx)` the q-th top-k candidate of rank r / column set `set`.
-template <class LsumF, class TgtF, class TopF>
+// T = double: the check mode and the statistics-in-the-middle path (1e-5 parity); T = float: the fused bf16 path, whose tolerance is
+// 1e-2 -- the ~100 dependent operations per row are then 1-2 us of latency instead of the 16 us the fp64 pipe takes.
+template <class T, class LsumF, class TgtF, class TopF>
 __device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int n_ranks, LsumF lsum_at, TgtF tgt_at, TopF top_at, float& loss_out, float (&cO)[2],
                                               float (&cT)[2], int& nw_out, int32_t* wslot_out, uint8_t* wrow_out) {
   const int n = a.n, k = a.k;
@@ -561,32 +578,32 @@ __device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int 
   cO[0] = cO[1] = cT[0] = cT[1] = 0.f;
   int nw = 0;
   if (!outl) {
-    const double s = a.scale, M = a.fixed_max, m = a.margin;
+    const T s = (T)a.scale, M = (T)a.fixed_max, m = (T)a.margin, cm = (T)a.cos_m, sm = (T)a.sin_m, one = (T)1;
     for (int l = 0; l < 2; ++l) {
-      double ct = tgt_at(l);
+      T ct = (T)tgt_at(l);
       // bf16 operands are rounded, so a cosine of two (nearly) identical unit vectors can land a few ulp outside
       // [-1, 1] and turn ffc.py:101's sqrt into NaN where the fp32 reference is finite: keep it strictly inside.
       // The fp32 check mode does not clamp and propagates NaN exactly like the reference.
-      if (a.use_bf16_rows) ct = fmin(fmax(ct, -1.0 + 1e-6), 1.0 - 1e-6);
-      double ft, dft;
+      if (a.use_bf16_rows) ct = fmin(fmax(ct, (T)(-1.0 + 1e-6)), (T)(1.0 - 1e-6));
+      T ft, dft;
       if (a.loss_type == FFC_LOSS_AM) {
         ft = ct - m;
-        dft = 1.0;
+        dft = one;
       } else if (a.loss_type == FFC_LOSS_ARC) {
-        const double sn = sqrt(1.0 - ct * ct);      // NaN for |ct| > 1, like ffc.py:101
-        ft = ct * cos(m) - sn * sin(m);
-        dft = cos(m) + ct * sin(m) / sn;
+        const T sn = sqrt((one - ct) * (one + ct));      // = sqrt(1 - ct^2) without the cancellation; NaN for |ct| > 1, like ffc.py:101
+        ft = ct * cm - sn * sm;
+        dft = cm + ct * sm / sn;
       } else {
         ft = ct > m ? ct - m : ct;
-        dft = 1.0;
+        dft = one;
       }
-      const double zt = s * ft;
-      const double et = exp(zt - M);
+      const T zt = s * ft;
+      const T et = exp(zt - M);
       const int cs = a.loss_type == FFC_LOSS_SV ? l : 0;   // common-statistics slot
-      const double L = (double)lsum_at(cs) + (double)lsum_at(2 + l) + et;
-      loss += (float)((log(L) + M - zt) / (double)n_pos);
-      cO[l] = (float)(s / L / (double)n_pos);
-      cT[l] = (float)(s * (et / L - 1.0) * dft / (double)n_pos);
+      const T L = (T)lsum_at(cs) + (T)lsum_at(2 + l) + et;
+      loss += (float)((log(L) + M - zt) / (T)n_pos);
+      cO[l] = (float)(s / L / (T)n_pos);
+      cT[l] = (float)(s * (et / L - one) * dft / (T)n_pos);
     }
   } else {
     // merge top-k candidates per loss: common (all ranks) + side_l (all ranks)
@@ -635,7 +652,7 @@ __global__ void __launch_bounds__(128) head_row_coef_kernel(const FinalizeArgs a
   if (i >= n) return;
   float loss, cO[2], cT[2];
   int nw;
-  row_coef_math(
+  row_coef_math<double>(
       a, i, a.n_ranks, [&](int slot) { return a.lsum[slot * n + i]; }, [&](int l) { return a.tgt[l * n + i]; },
       [&](int r, int set, int q, float& v, int32_t& idx) {
         const int64_t base = ((((int64_t)r * 3 + set) * n) + i) * k;
@@ -692,135 +709,189 @@ __global__ void __launch_bounds__(128) head_reduce_scalars_kernel(const ReduceJo
   }
 }
 
+// One prototype row as the fused finalize reads it: the bf16 mirror row, or (overlay) an fp32 row rounded on the fly.
+struct WRow {
+  const __nv_bfloat16* h;
+  const float* f;
+};
+__device__ __forceinline__ WRow w_row(const FinalizeArgs& a, int r, int64_t loc) {
+  WRow w;
+  const int64_t e = (int64_t)r * a.q_local + loc;
+  w.h = a.qh + e * a.D;
+  w.f = nullptr;
+  if (a.ovl_map) {
+    const int32_t c = __ldg(a.ovl_map + e);
+    if (c >= 0) w.f = (c & 0x40000000) ? a.ovl_undo + (int64_t)(c & 0x3fffffff) * a.D : a.ovl_g + (int64_t)c * a.D;
+  }
+  return w;
+}
+__device__ __forceinline__ float4 w_load4(const WRow& w, int d) {
+  if (w.f) {
+    const float4 v = *reinterpret_cast<const float4*>(w.f + d);
+    return make_float4(__bfloat162float(__float2bfloat16(v.x)), __bfloat162float(__float2bfloat16(v.y)), __bfloat162float(__float2bfloat16(v.z)),
+                       __bfloat162float(__float2bfloat16(v.w)));
+  }
+  const uint2 u = *reinterpret_cast<const uint2*>(w.h + d);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 a2 = __bfloat1622float2(lo), b2 = __bfloat1622float2(hi);
+  return make_float4(a2.x, a2.y, b2.x, b2.y);
+}
+
 // Fast path of the bf16 AM / Arc head: chunk reduction of the three sweeps' partials, the scalar part and dLoss/dp in ONE
-// launch (block = row).  No osum round trip through HBM; replaces reduce + row_coef + finalize.
+// launch.  No osum round trip through HBM; replaces reduce + row_coef + finalize.  A block takes FR = 16 rows:
+//   phase 1 (GATHERED = false only): one thread per (row, sweep) sums the chunk denominators and merges the chunk top-k lists;
+//   phase 2: one THREAD per row does the scalar part (margin function, log / exp, top-k merge over ranks) -- in fp32, all rows of
+//            the grid side by side (one lane per row on the fp64 pipe cost 16 us per row, 3.5 waves of it at 8 192 rows);
+//   phase 3: one warp per row, lanes over D: chunk sums of the three O partials, the two prototype rows of the target (or the
+//            hard-negative rows of an outlier row), 16-byte stores -- the bandwidth part, ~(chunks * 3 + 2) * D * 4 bytes per row.
 //   GATHERED = false (one GPU): the scalars are reduced here from the partials as well;
 //   GATHERED = true (sharded head): the scalars come from the n_ranks gathered records (`rec`, `rec_stride` words apart),
-//     summed in rank order on every rank; O is this rank's partial, so dp is this rank's contribution (reduce-scattered next).
+//     summed in rank order on every rank; O is this rank's partial, so dp is this rank's contribution -- stored locally for a
+//     reduce-scatter, or (dp_peer) straight into the owner rank's staging buffer.
+constexpr int FR = 16;
 template <bool GATHERED>
 __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a, const float* __restrict__ rec,
                                                                   int64_t rec_stride) {
-  // One WARP per row (4 rows per block): the scalar part is ~1000 dependent fp64 operations on one lane (16 us on this part's
-  // fp64 pipe), so rows must run side by side -- with a block per row 8 192 rows took 3.5 waves of that latency (130 us).
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 4 + w, n = a.n, D = a.D, k = a.k;
-  if (i >= n) return;
-  __shared__ float s_l[4][3];
-  __shared__ float s_tv[4][3][KMAX];
-  __shared__ int32_t s_ti[4][3][KMAX];
-  __shared__ float s_coef[4][4];
-  __shared__ int s_nw[4];
-  __shared__ int32_t s_wslot[4][2 * KMAX];
-  __shared__ uint8_t s_wrow[4][2 * KMAX];
-  const bool outl = a.is_out[i];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * FR, n = a.n, D = a.D, k = a.k;
+  __shared__ float s_l[FR][3];
+  __shared__ float s_tv[FR][3][KMAX];
+  __shared__ int32_t s_ti[FR][3][KMAX];
+  __shared__ float s_coef[FR][4];
+  __shared__ int s_nw[FR];
+  __shared__ int32_t s_wslot[FR][2 * KMAX];
+  __shared__ uint8_t s_wrow[FR][2 * KMAX];
   if (!GATHERED) {
-    if (lane < 3) {
-      const ReduceJob& r = jobs.j[lane];
-      float acc = 0.f;
-      for (int c = 0; c < r.n_chunks; ++c) acc += r.l_part[(int64_t)c * n + i];
-      s_l[w][lane] = acc;
-      float tv[KMAX];
-      int32_t ti[KMAX];
-      for (int q = 0; q < KMAX; ++q) {
-        tv[q] = -INFINITY;
-        ti[q] = -1;
-      }
-      if (outl) {
-        for (int c = 0; c < r.n_chunks; ++c)
-          for (int q = 0; q < k; ++q) {
-            const float v = r.topv_part[((int64_t)c * n + i) * k + q];
-            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, r.topi_part[((int64_t)c * n + i) * k + q]);
-          }
-      }
-      for (int q = 0; q < KMAX; ++q) {
-        int32_t id = ti[q];
-        if (id >= 0) id = (int32_t)(r.idx_base + (r.idx_map ? r.idx_map[id] : id));   // -> global slot
-        s_tv[w][lane][q] = tv[q];
-        s_ti[w][lane][q] = id;
+    if (tid < FR * 3) {
+      const int r = tid / 3, j = tid - 3 * r, i = row0 + r;
+      if (i < n) {
+        const ReduceJob& rj = jobs.j[j];
+        float acc = 0.f;
+        for (int c = 0; c < rj.n_chunks; ++c) acc += rj.l_part[(int64_t)c * n + i];
+        s_l[r][j] = acc;
+        float tv[KMAX];
+        int32_t ti[KMAX];
+        for (int q = 0; q < KMAX; ++q) {
+          tv[q] = -INFINITY;
+          ti[q] = -1;
+        }
+        if (a.is_out[i]) {
+          for (int c = 0; c < rj.n_chunks; ++c)
+            for (int q = 0; q < k; ++q) {
+              const float v = rj.topv_part[((int64_t)c * n + i) * k + q];
+              if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, rj.topi_part[((int64_t)c * n + i) * k + q]);
+            }
+        }
+        for (int q = 0; q < KMAX; ++q) {
+          int32_t id = ti[q];
+          if (id >= 0) id = (int32_t)(rj.idx_base + (rj.idx_map ? rj.idx_map[id] : id));   // -> global slot
+          s_tv[r][j][q] = tv[q];
+          s_ti[r][j][q] = id;
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (tid < FR && row0 + tid < n) {
+    const int r = tid, i = row0 + r;
     float loss, cO[2], cT[2];
     int nw;
     if (GATHERED) {
       const int R = a.n_ranks;
-      row_coef_math(
+      row_coef_math<float>(
           a, i, R,
           [&](int slot) {
             float acc = 0.f;
-            for (int r = 0; r < R; ++r) acc += rec[r * rec_stride + (int64_t)slot * n + i];
+            for (int q = 0; q < R; ++q) acc += rec[q * rec_stride + (int64_t)slot * n + i];
             return acc;
           },
           [&](int l) {
             float acc = 0.f;
-            for (int r = 0; r < R; ++r) acc += rec[r * rec_stride + (int64_t)(4 + l) * n + i];
+            for (int q = 0; q < R; ++q) acc += rec[q * rec_stride + (int64_t)(4 + l) * n + i];
             return acc;
           },
-          [&](int r, int set, int q, float& v, int32_t& idx) {
-            const float* base = rec + r * rec_stride + 8 * (int64_t)n;
-            const int64_t e = ((int64_t)set * n + i) * k + q;
-            v = base[e];
-            idx = reinterpret_cast<const int32_t*>(base + 3 * (int64_t)n * k)[e];
+          [&](int q, int set, int e, float& v, int32_t& idx) {
+            const float* base = rec + q * rec_stride + 8 * (int64_t)n;
+            const int64_t o = ((int64_t)set * n + i) * k + e;
+            v = base[o];
+            idx = reinterpret_cast<const int32_t*>(base + 3 * (int64_t)n * k)[o];
           },
-          loss, cO, cT, nw, s_wslot[w], s_wrow[w]);
+          loss, cO, cT, nw, s_wslot[r], s_wrow[r]);
     } else {
-      row_coef_math(
-          a, i, 1, [&](int slot) { return slot == 0 ? s_l[w][0] : (slot >= 2 ? s_l[w][slot - 1] : 0.f); }, [&](int l) { return a.tgt[l * n + i]; },
-          [&](int, int set, int q, float& v, int32_t& idx) {
-            v = s_tv[w][set][q];
-            idx = s_ti[w][set][q];
+      row_coef_math<float>(
+          a, i, 1, [&](int slot) { return slot == 0 ? s_l[r][0] : (slot >= 2 ? s_l[r][slot - 1] : 0.f); }, [&](int l) { return a.tgt[l * n + i]; },
+          [&](int, int set, int e, float& v, int32_t& idx) {
+            v = s_tv[r][set][e];
+            idx = s_ti[r][set][e];
           },
-          loss, cO, cT, nw, s_wslot[w], s_wrow[w]);
+          loss, cO, cT, nw, s_wslot[r], s_wrow[r]);
     }
     a.row_loss[i] = loss;
-    s_coef[w][0] = cO[0];
-    s_coef[w][1] = cO[1];
-    s_coef[w][2] = cT[0];
-    s_coef[w][3] = cT[1];
-    s_nw[w] = nw;
+    s_coef[r][0] = cO[0];
+    s_coef[r][1] = cO[1];
+    s_coef[r][2] = cT[0];
+    s_coef[r][3] = cT[1];
+    s_nw[r] = nw;
   }
-  __syncwarp();
-  const float cO0 = s_coef[w][0], cO1 = s_coef[w][1], cT0 = s_coef[w][2], cT1 = s_coef[w][3];
-  const int32_t tc = a.tcol[i];
-  const int trow2 = (a.tpos[i] >= 0) ? 1 : 0;
-  const int nw = s_nw[w];
-  for (int d = lane * 4; d < D; d += 32 * 4) {
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!outl) {
-      float o[3][4];
-#pragma unroll
-      for (int jb = 0; jb < 3; ++jb) {
-        const ReduceJob& r = jobs.j[jb];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 0; c < r.n_chunks; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(r.o_part + ((int64_t)c * n + i) * D + d);
-          acc.x += v.x;
-          acc.y += v.y;
-          acc.z += v.z;
-          acc.w += v.w;
-        }
-        o[jb][0] = acc.x;
-        o[jb][1] = acc.y;
-        o[jb][2] = acc.z;
-        o[jb][3] = acc.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        g[e] = cO0 * (o[0][e] + o[1][e]) + cO1 * (o[0][e] + o[2][e]);
-        if (tc >= 0) g[e] += cT0 * w_elem(a, 0, tc, d + e) + cT1 * w_elem(a, trow2, tc, d + e);
-      }
-    } else {
-      for (int x = 0; x < nw; ++x) {
-        const int64_t loc = (int64_t)s_wslot[w][x] - a.col_offset;
-        if (loc >= 0 && loc < a.q_local) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) g[e] += cO0 * w_elem(a, s_wrow[w][x], loc, d + e);
-        }
-      }
+  __syncthreads();
+  for (int r = w; r < FR; r += 4) {
+    const int i = row0 + r;
+    if (i >= n) break;
+    const bool outl = a.is_out[i];
+    const float cO0 = s_coef[r][0], cO1 = s_coef[r][1], cT0 = s_coef[r][2], cT1 = s_coef[r][3];
+    const int32_t tc = a.tcol[i];
+    const int nw = s_nw[r];
+    float* out = a.dp_peer ? a.dp_peer[i / a.dp_rows_per_rank] + a.dp_slot_off + (int64_t)(i % a.dp_rows_per_rank) * D : a.dp + (int64_t)i * D;
+    WRow t0, t1;
+    t0.h = t1.h = nullptr;
+    t0.f = t1.f = nullptr;
+    if (!outl && tc >= 0) {
+      t0 = w_row(a, 0, tc);
+      t1 = w_row(a, (a.tpos[i] >= 0) ? 1 : 0, tc);
     }
-    *reinterpret_cast<float4*>(a.dp + (int64_t)i * D + d) = make_float4(g[0], g[1], g[2], g[3]);
+    for (int d = lane * 4; d < D; d += 32 * 4) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!outl) {
+        float o[3][4];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          const ReduceJob& rj = jobs.j[jb];
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < rj.n_chunks; ++c) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(rj.o_part + ((int64_t)c * n + i) * D + d));
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+          }
+          o[jb][0] = acc.x;
+          o[jb][1] = acc.y;
+          o[jb][2] = acc.z;
+          o[jb][3] = acc.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[e] = cO0 * (o[0][e] + o[1][e]) + cO1 * (o[0][e] + o[2][e]);
+        if (tc >= 0) {
+          const float4 w0 = w_load4(t0, d), w1 = w_load4(t1, d);
+          g[0] += cT0 * w0.x + cT1 * w1.x;
+          g[1] += cT0 * w0.y + cT1 * w1.y;
+          g[2] += cT0 * w0.z + cT1 * w1.z;
+          g[3] += cT0 * w0.w + cT1 * w1.w;
+        }
+      } else {
+        for (int x = 0; x < nw; ++x) {
+          const int64_t loc = (int64_t)s_wslot[r][x] - a.col_offset;
+          if (loc >= 0 && loc < a.q_local) {
+            const float4 wv = w_load4(w_row(a, s_wrow[r][x], loc), d);
+            g[0] += cO0 * wv.x;
+            g[1] += cO0 * wv.y;
+            g[2] += cO0 * wv.z;
+            g[3] += cO0 * wv.w;
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(out + d) = make_float4(g[0], g[1], g[2], g[3]);
+    }
   }
 }
 
@@ -1230,6 +1301,8 @@ static FinalizeArgs make_finalize_args(ffc_head_t* h, const ffc_head_pass* in, c
   a.scale = c.scale;
   a.margin = c.margin;
   a.fixed_max = fixed_max_of(c);
+  a.cos_m = cos((double)c.margin);
+  a.sin_m = sin((double)c.margin);
   a.row_loss = h->row_loss;
   a.dp = dp_out;
   return a;
@@ -1244,7 +1317,7 @@ static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_
   if (h->jobs_pending) {       // one-GPU fast path: the sweep left its partials for the fused reduce + finalize
     FFC_REQUIRE(n_ranks_topk == 1, "fused finalize is single-rank");
     h->jobs_pending = 0;
-    head_finalize_fused_kernel<false><<<(a.n + 3) / 4, 128, 0, s>>>(*h->jobs, a, nullptr, 0);
+    head_finalize_fused_kernel<false><<<(a.n + FR - 1) / FR, 128, 0, s>>>(*h->jobs, a, nullptr, 0);
     FFC_LAUNCH_CHECK();
   } else {
     head_row_coef_kernel<<<(a.n + 127) / 128, 128, 0, s>>>(a, h->coef, h->nslot, h->wslot, h->wrow);
@@ -1286,13 +1359,29 @@ extern "C" int ffc_head_sweep_record(ffc_head_t* h, const ffc_head_pass* in, voi
 
 extern "C" int ffc_head_finalize_gathered(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks, int64_t record_stride_words,
                                           float* loss_out, float* dp_out, void* stream) {
-  FFC_REQUIRE(h && in && records && loss_out && dp_out && n_ranks >= 1, "ffc_head_finalize_gathered: bad arguments");
+  return ffc_head_finalize_gathered_ex(h, in, records, n_ranks, record_stride_words, nullptr, loss_out, dp_out, stream);
+}
+
+extern "C" int ffc_head_finalize_gathered_ex(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks, int64_t record_stride_words,
+                                             const ffc_head_finalize_opts* opts, float* loss_out, float* dp_out, void* stream) {
+  FFC_REQUIRE(h && in && records && loss_out && n_ranks >= 1, "ffc_head_finalize_gathered: bad arguments");
+  FFC_REQUIRE(dp_out || (opts && opts->dp_peer), "ffc_head_finalize_gathered: neither dp_out nor peer staging buffers given");
   FFC_REQUIRE(h->jobs_pending, "ffc_head_finalize_gathered: no ffc_head_sweep_record pending");
   FFC_REQUIRE(record_stride_words >= record_words(in->n_rows, h->cfg.topk), "ffc_head_finalize_gathered: record stride too small");
   cudaStream_t s = (cudaStream_t)stream;
-  const FinalizeArgs a = make_finalize_args(h, in, nullptr, n_ranks, dp_out);
+  FinalizeArgs a = make_finalize_args(h, in, nullptr, n_ranks, dp_out);
+  if (opts) {
+    FFC_REQUIRE(!opts->overlay_map || (opts->overlay_g && opts->overlay_undo), "ffc_head_finalize_gathered_ex: overlay map without its row tables");
+    FFC_REQUIRE(!opts->dp_peer || opts->dp_rows_per_rank >= 1, "ffc_head_finalize_gathered_ex: dp_rows_per_rank must be >= 1");
+    a.ovl_map = opts->overlay_map;
+    a.ovl_g = opts->overlay_g;
+    a.ovl_undo = opts->overlay_undo;
+    a.dp_peer = opts->dp_peer;
+    a.dp_rows_per_rank = opts->dp_rows_per_rank;
+    a.dp_slot_off = opts->dp_slot_offset;
+  }
   h->jobs_pending = 0;
-  head_finalize_fused_kernel<true><<<(a.n + 3) / 4, 128, 0, s>>>(*h->jobs, a, (const float*)records, record_stride_words);
+  head_finalize_fused_kernel<true><<<(a.n + FR - 1) / FR, 128, 0, s>>>(*h->jobs, a, (const float*)records, record_stride_words);
   FFC_LAUNCH_CHECK();
   head_loss_sum_kernel<<<1, 1024, 0, s>>>(h->row_loss, a.n, loss_out);
   FFC_LAUNCH_CHECK();

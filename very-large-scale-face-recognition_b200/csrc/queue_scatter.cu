@@ -26,11 +26,20 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
 
 __global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ qf, __nv_bfloat16* __restrict__ qh, const int32_t* __restrict__ rows,
                                                             const int32_t* __restrict__ cols, const float* __restrict__ g, int B, int64_t Q, int D,
-                                                            float* __restrict__ undo, const int32_t* __restrict__ src_row) {
+                                                            float* __restrict__ undo, const int32_t* __restrict__ src_row,
+                                                            int32_t* __restrict__ ovl_map, int ovl_table) {
   const int i = blockIdx.x;
   if (cols[i] < 0) return;   // padded position (sharded callers)
   if (later_duplicate(rows, cols, i, B)) return;
   const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
+  if (ovl_map && threadIdx.x == 0) {
+    // overlay of the sharded head's merged step (csrc/head.cu FinalizeArgs::ovl_map): where the sweep-time content of this (row, slot)
+    // will still be found after later writes.  Table 0 (this enqueue's own source row, a rollback pass) always wins; table 1 (the
+    // previous content this enqueue saves in undo[i], the commit pass that follows) only marks entries no rollback enqueue holds.
+    int32_t* m = ovl_map + (int64_t)rows[i] * Q + cols[i];
+    if (ovl_table == 0) *m = src_row ? src_row[i] : i;
+    else if (*m < 0) *m = 0x40000000 | i;
+  }
   const float4* src = reinterpret_cast<const float4*>(g + (int64_t)(src_row ? src_row[i] : i) * D);
   float4* dst = reinterpret_cast<float4*>(qf + off);
   float4* und = undo ? reinterpret_cast<float4*>(undo + (int64_t)i * D) : nullptr;
@@ -148,19 +157,67 @@ extern "C" int ffc_queue_scatter(float* queue_f32_dev, void* queue_bf16_dev, con
   FFC_REQUIRE(g_dev != nullptr, "ffc_queue_scatter: g is NULL");
   if (B == 0) return FFC_OK;
   queue_scatter_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, g_dev, B, Q, D,
-                                                             undo_f32_dev, nullptr);
+                                                             undo_f32_dev, nullptr, nullptr, 0);
   FFC_LAUNCH_CHECK();
   return FFC_OK;
 }
 
 extern "C" int ffc_queue_scatter_indexed(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev, const int32_t* cols_dev,
                                          const float* g_dev, const int32_t* src_row_dev, int B, int64_t Q, int D, float* undo_f32_dev, void* stream) {
+  return ffc_queue_scatter_overlay(queue_f32_dev, queue_bf16_dev, rows_dev, cols_dev, g_dev, src_row_dev, B, Q, D, undo_f32_dev, nullptr, 0, stream);
+}
+
+extern "C" int ffc_queue_scatter_overlay(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev, const int32_t* cols_dev,
+                                         const float* g_dev, const int32_t* src_row_dev, int B, int64_t Q, int D, float* undo_f32_dev,
+                                         int32_t* overlay_map_dev, int overlay_table, void* stream) {
   int rc = check_scatter_args(queue_f32_dev, rows_dev, cols_dev, B, Q, D);
   if (rc) return rc;
   FFC_REQUIRE(g_dev != nullptr && src_row_dev != nullptr, "ffc_queue_scatter_indexed: NULL argument");
+  FFC_REQUIRE(!overlay_map_dev || overlay_table == 0 || (overlay_table == 1 && undo_f32_dev), "ffc_queue_scatter_overlay: table 1 marks need the undo buffer");
   if (B == 0) return FFC_OK;
   queue_scatter_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, g_dev, B, Q, D,
-                                                             undo_f32_dev, src_row_dev);
+                                                             undo_f32_dev, src_row_dev, overlay_map_dev, overlay_table);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+namespace ffc {
+__global__ void __launch_bounds__(256) overlay_clear_kernel(int32_t* __restrict__ map, const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int n,
+                                                            int64_t Q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && cols[i] >= 0) map[(int64_t)rows[i] * Q + cols[i]] = -1;
+}
+
+// out[e] = sum over r (in rank order: deterministic) of slabs[r * stride + e]: the local half of the reduce-scatter that finalize's
+// peer stores started
+__global__ void __launch_bounds__(256) sum_slabs_kernel(const float4* __restrict__ slabs, int n_slabs, int64_t stride4, int64_t n4, float4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = __ldcs(slabs + i);
+    for (int r = 1; r < n_slabs; ++r) {
+      const float4 v = __ldcs(slabs + r * stride4 + i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    out[i] = acc;
+  }
+}
+}  // namespace ffc
+
+extern "C" int ffc_overlay_clear(int32_t* overlay_map_dev, const int32_t* rows_dev, const int32_t* cols_dev, int n, int64_t Q, void* stream) {
+  FFC_REQUIRE(overlay_map_dev && rows_dev && cols_dev && n >= 0 && Q >= 1, "ffc_overlay_clear: bad arguments");
+  if (n == 0) return FFC_OK;
+  overlay_clear_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(overlay_map_dev, rows_dev, cols_dev, n, Q);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_sum_slabs(const float* slabs_dev, int n_slabs, int64_t slab_stride, int64_t n, float* out_dev, void* stream) {
+  FFC_REQUIRE(slabs_dev && out_dev && n_slabs >= 1 && n >= 0 && n % 4 == 0 && slab_stride % 4 == 0, "ffc_sum_slabs: bad arguments (n and the stride must be multiples of 4)");
+  if (n == 0) return FFC_OK;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(n / 4, 256), 148 * 8);
+  sum_slabs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)slabs_dev, n_slabs, slab_stride / 4, n / 4, (float4*)out_dev);
   FFC_LAUNCH_CHECK();
   return FFC_OK;
 }

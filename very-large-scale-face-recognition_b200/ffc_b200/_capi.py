@@ -32,6 +32,11 @@ class HeadStats(C.Structure):
     _fields_ = [('lsum', c_void_p), ('osum', c_void_p), ('tgt', c_void_p), ('topv', c_void_p), ('topi', c_void_p)]
 
 
+class FinalizeOpts(C.Structure):
+    _fields_ = [('overlay_map', c_void_p), ('overlay_g', c_void_p), ('overlay_undo', c_void_p), ('dp_peer', c_void_p),
+                ('dp_rows_per_rank', c_int32), ('dp_slot_offset', c_int64)]
+
+
 class TailArgs(C.Structure):
     _fields_ = [('x', c_void_p), ('p', c_void_p), ('p_stride', c_int64), ('inv_norm', c_void_p), ('n_rows', c_int32), ('feat_dim', c_int32),
                 ('mode', c_int32), ('eps', c_float), ('momentum', c_float), ('gamma', c_void_p), ('beta', c_void_p),
@@ -69,6 +74,10 @@ PROTOTYPES = {
     'ffc_head_sweep_record': (c_int, [c_void_p, C.POINTER(HeadPass), c_void_p, c_void_p]),
     'ffc_head_finalize_gathered': (c_int, [c_void_p, C.POINTER(HeadPass), c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'ffc_queue_scatter_indexed': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    'ffc_queue_scatter_overlay': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'ffc_overlay_clear': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    'ffc_sum_slabs': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    'ffc_head_finalize_gathered_ex': (c_int, [c_void_p, C.POINTER(HeadPass), c_void_p, c_int, c_int64, C.POINTER(FinalizeOpts), c_void_p, c_void_p, c_void_p]),
     'ffc_route_keys': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ffc_ema_chunk_elems': (c_int, []),
     'ffc_ema_update': (c_int, [c_void_p, c_int, c_float, c_float, c_void_p]),

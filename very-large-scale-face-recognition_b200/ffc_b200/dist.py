@@ -1,7 +1,7 @@
 """Column-sharded FFC head over the GPUs of one node (partial-FC style; nothing like it exists in the reference,
 which is single-process -- SURVEY.md section 8(e)).
 
-Partition: rank r of R owns queue slots [r*Q/R, (r+1)*Q/R) -- fp32 rows, bf16 mirror, queue positions -- and the
+Partition: rank r of R owns a contiguous range of about Q/R queue slots (the first Q mod R ranks one more) -- fp32 rows, bf16 mirror, queue positions -- and the
 LRU of the identities with ``id mod R == r`` (an exact, balanced "identity hash" for dense class indices).  A rank's
 LRU is bit-exact with the reference ``LRU(Q/R)`` fed the keys it owns in global batch order (rank-major, then row).
 
@@ -22,6 +22,7 @@ CPU (gloo, world_size 2) by the tests with a torch stand-in; the product backend
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -51,9 +52,10 @@ class CudaShardBackend:
             self.queue = q
             self.queue_bf16 = torch.empty(2, Ql, D, dtype=torch.bfloat16, device=dev)
             self.qpos = torch.zeros(Ql, dtype=torch.uint8, device=dev)
-            # per-pass bookkeeping state, two sets: the next pass's bookkeeping may overlap the current pass's sweep
+            # per-pass bookkeeping state, three sets: 1 = commit pass; 0 and 2 = the rollback passes of alternating steps (the next
+            # step's rollback bookkeeping -- label prefetch -- is computed while the current step still needs its own)
             self._sets = [dict(cmask=torch.zeros((Ql + 31) // 32 + 8, **i32), rows=torch.zeros(n, **i32), cols=torch.full((n,), -1, **i32),
-                               ones_list=torch.empty(n, **i32), n_ones=torch.zeros(1, **i32)) for _ in range(2)]
+                               ones_list=torch.empty(n, **i32), n_ones=torch.zeros(1, **i32), n=0) for _ in range(3)]
             self.use_set(0)
             self.undo_rows = torch.empty(n, D, **f32)
             cfg = HeadConfig(n, Ql, q_total, col_offset, D, _capi.LOSS_TYPES[loss_type], scale, margin, topk, _capi.PRECISIONS[precision])
@@ -61,21 +63,33 @@ class CudaShardBackend:
             check(self.lib.ffc_head_create(C.byref(cfg), C.byref(h)))
             self._h, self._cfg = h, cfg
             self.record_path = precision == 'bf16' and loss_type in ('AM', 'Arc')
+            # merged step (one statistics exchange per FFC.forward): both passes' sweep results are outstanding at once, so the commit
+            # pass gets its own head workspace; the rollback pass's finalize reads rewritten queue rows through the overlay map
+            self.merged = self.record_path
+            self._h2 = None
+            if self.merged:
+                h2 = C.c_void_p()
+                check(self.lib.ffc_head_create(C.byref(cfg), C.byref(h2)))
+                self._h2 = h2
+                self.undo_rows_cm = torch.empty(n, D, **f32)
+                self.ovl_map = torch.full((2 * Ql,), -1, **i32)
         self.sync_mirror()
 
     def __del__(self):
-        h = self.__dict__.pop('_h', None)
-        if h:
-            try:
-                self.lib.ffc_head_destroy(h)
-            except Exception:
-                pass
+        for name in ('_h', '_h2'):
+            h = self.__dict__.pop(name, None)
+            if h:
+                try:
+                    self.lib.ffc_head_destroy(h)
+                except Exception:
+                    pass
 
     def _s(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def use_set(self, i):
         st = self._sets[i]
+        self._set = st
         self.cmask, self.rows, self.cols, self.ones_list, self.n_ones = st['cmask'], st['rows'], st['cols'], st['ones_list'], st['n_ones']
 
     def sync_mirror(self):
@@ -99,7 +113,7 @@ class CudaShardBackend:
         self.cols[:n].fill_(-1)
         self.lru.assign(keys_compact, journal=journal, qpos=self.qpos, rows=self.rows, cols=self.cols, ones_list=self.ones_list,
                         n_ones=self.n_ones, cmask=self.cmask, n_dev=n_dev)
-        self._n = n
+        self._set['n'] = n
 
     def route(self, keys_all, n_ranks, rank):
         """Stable partition of the gathered gallery keys: this rank's keys first (global batch order).  One launch."""
@@ -110,12 +124,21 @@ class CudaShardBackend:
         check(self.lib.ffc_route_keys(keys_all.data_ptr(), n, n_ranks, rank, keys_c.data_ptr(), order.data_ptr(), n_mine.data_ptr(), self._s()))
         return keys_c, order, n_mine
 
-    def scatter(self, g_all, order, save_undo):
-        """Enqueue this rank's gallery rows straight out of the all-gathered embeddings (row j of the bookkeeping <- g_all[order[j]])."""
+    def scatter(self, g_all, order, save_undo, overlay_table=None):
+        """Enqueue this rank's gallery rows straight out of the all-gathered embeddings (row j of the bookkeeping <- g_all[order[j]]).
+        overlay_table (merged step): 0 = a rollback pass's enqueue, 1 = the commit pass's enqueue that follows it in the same step --
+        every winning write is recorded in the overlay map (see ffc_queue_scatter_overlay); the commit pass then saves the rows it
+        replaces in its own undo buffer."""
         assert g_all.dtype == torch.float32 and g_all.is_contiguous() and order.dtype == torch.int32
-        check(self.lib.ffc_queue_scatter_indexed(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
-                                                 g_all.data_ptr(), order.data_ptr(), self._n, self.Ql, self.D,
-                                                 self.undo_rows.data_ptr() if save_undo else None, self._s()))
+        undo = (self.undo_rows_cm if overlay_table == 1 else self.undo_rows) if save_undo else None
+        check(self.lib.ffc_queue_scatter_overlay(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+                                                 g_all.data_ptr(), order.data_ptr(), self._set['n'], self.Ql, self.D,
+                                                 None if undo is None else undo.data_ptr(),
+                                                 None if overlay_table is None else self.ovl_map.data_ptr(), overlay_table or 0, self._s()))
+
+    def overlay_clear(self, set_idx):
+        st = self._sets[set_idx]
+        check(self.lib.ffc_overlay_clear(self.ovl_map.data_ptr(), st['rows'].data_ptr(), st['cols'].data_ptr(), st['n'], self.Ql, self._s()))
 
     def undo_bookkeeping(self):
         """lru.py:252-255 + ffc.py:256-257: the LRU / queue positions of a rollback pass can be restored as soon as the probe
@@ -124,7 +147,7 @@ class CudaShardBackend:
 
     def restore_queue(self):
         check(self.lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
-                                         self.undo_rows.data_ptr(), self._n, self.Ql, self.D, self._s()))
+                                         self.undo_rows.data_ptr(), self._set['n'], self.Ql, self.D, self._s()))
 
     def view(self, keys):
         return self.lru.view_batch(keys)
@@ -138,27 +161,43 @@ class CudaShardBackend:
         return hp, hs
 
     # -- record path (one all-gather per pass instead of all-reduce + all-gather; see include/ffc_b200.h) --------------------
-    def new_records(self, n, n_ranks):
+    def new_records(self, n, n_ranks, passes=1):
+        """Record buffers: `own` [passes, words] written by sweep_record, `all` [n_ranks, passes, words] filled by ONE all-gather."""
         w = C.c_int64()
         check(self.lib.ffc_head_record_words(C.byref(self._cfg), n, C.byref(w)))
-        return dict(own=torch.empty(w.value, dtype=torch.float32, device=self.dev),
-                    all=torch.empty(n_ranks, w.value, dtype=torch.float32, device=self.dev), words=w.value)
+        return dict(own=torch.empty(passes, w.value, dtype=torch.float32, device=self.dev),
+                    all=torch.empty(n_ranks, passes, w.value, dtype=torch.float32, device=self.dev), words=w.value, passes=passes)
 
     def _pass_struct(self, p_all, label):
         return HeadPass(p_all.data_ptr(), self.queue.data_ptr(), self.queue_bf16.data_ptr(), label.data_ptr(), self.ones_list.data_ptr(),
                         self.n_ones.data_ptr(), self.cmask.data_ptr(), p_all.shape[0])
 
-    def sweep_record(self, p_all, label, rec):
+    def sweep_record(self, p_all, label, rec, which=0):
+        """prep + sweep + scalar reduction of one pass into rec['own'][which]; pass `which` (0 rollback / 1 commit of a merged step) uses
+        its own head workspace, so both passes' partial results can be outstanding until the step's single exchange"""
         hp = self._pass_struct(p_all, label)
-        check(self.lib.ffc_head_sweep_record(self._h, C.byref(hp), rec['own'].data_ptr(), self._s()))
+        check(self.lib.ffc_head_sweep_record(self._h2 if which else self._h, C.byref(hp), rec['own'][which].data_ptr(), self._s()))
 
-    def finalize_gathered(self, p_all, label, rec, n_ranks):
+    def finalize_gathered(self, p_all, label, rec, n_ranks, which=0, overlay_g=None, route=None):
+        """finalize of pass `which` from the gathered records.  overlay_g: the gathered gallery embeddings of this (rollback) pass -- its
+        queue rows have been restored / re-enqueued since the sweep and are read through the overlay map.  route = (peer pointer table,
+        rows per rank, slot offset): dLoss/dp rows go straight to their owner rank's staging buffer (no dp tensor is returned)."""
         hp = self._pass_struct(p_all, label)
-        dp = torch.empty(p_all.shape[0], self.D, dtype=torch.float32, device=self.dev)
         loss = torch.empty((), dtype=torch.float32, device=self.dev)
-        check(self.lib.ffc_head_finalize_gathered(self._h, C.byref(hp), rec['all'].data_ptr(), n_ranks, rec['words'], loss.data_ptr(), dp.data_ptr(),
-                                                  self._s()))
+        dp = None if route is not None else torch.empty(p_all.shape[0], self.D, dtype=torch.float32, device=self.dev)
+        opts = _capi.FinalizeOpts()
+        if overlay_g is not None:
+            assert overlay_g.dtype == torch.float32 and overlay_g.is_contiguous()
+            opts.overlay_map, opts.overlay_g, opts.overlay_undo = self.ovl_map.data_ptr(), overlay_g.data_ptr(), self.undo_rows_cm.data_ptr()
+        if route is not None:
+            opts.dp_peer, opts.dp_rows_per_rank, opts.dp_slot_offset = route[0].data_ptr(), int(route[1]), int(route[2])
+        w, passes = rec['words'], rec['passes']
+        check(self.lib.ffc_head_finalize_gathered_ex(self._h2 if which else self._h, C.byref(hp), rec['all'].data_ptr() + 4 * w * which, n_ranks,
+                                                     w * passes, C.byref(opts), loss.data_ptr(), None if dp is None else dp.data_ptr(), self._s()))
         return loss, dp
+
+    def sum_slabs(self, slabs, n_slabs, stride, n, out):
+        check(self.lib.ffc_sum_slabs(slabs.data_ptr(), n_slabs, stride, n, out.data_ptr(), self._s()))
 
     def sweep(self, p_all, label, st, rank_slot):
         hp, hs = self._structs(p_all, label, st, rank_slot)
@@ -229,11 +268,13 @@ class ShardedFFCHead:
         self.group = group
         self.R = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        assert queue_size % self.R == 0, 'queue_size must be divisible by the number of ranks'
-        self.D, self.Q, self.Ql = feat_dim, queue_size, queue_size // self.R
+        assert queue_size >= self.R, 'fewer queue slots than ranks'
+        # contiguous slot ranges, the first queue_size % R ranks one slot longer: any queue size shards (the reference's default is 7409, ffc.py:11)
+        base, rem = divmod(queue_size, self.R)
+        self.D, self.Q, self.Ql = feat_dim, queue_size, base + (1 if self.rank < rem else 0)
         self.B = max_batch
         self.k = hard_neg_k(queue_size)
-        self.off = self.rank * self.Ql
+        self.off = self.rank * base + min(self.rank, rem)
         n = self.R * self.B
         if backend_factory is None:
             self.backend = CudaShardBackend(feat_dim, self.Ql, queue_size, self.off, n, scale, loss_type, margin, self.k, precision, device)
@@ -243,7 +284,6 @@ class ShardedFFCHead:
             self.dev = torch.device('cpu')
         self._nccl = dist.get_backend(group) == 'nccl'
         self._stats = {}
-        import os
         self._timing = [] if (os.environ.get('FFC_DIST_TIMING') and self._nccl) else None
         self._side = torch.cuda.Stream(device=self.dev) if (self._nccl and not os.environ.get('FFC_DIST_NO_OVERLAP')) else None
         self._pre = None            # labels + rollback-pass bookkeeping of the next forward_pair (see prefetch)
@@ -257,6 +297,43 @@ class ShardedFFCHead:
             self._side_group = dist.new_group(ranks=ranks, backend='nccl')      # its communicator is built on first use (first prefetch)
         self._rb_done = None        # event: the last pass that used bookkeeping set 0 has finished with it
         self._lru_main_ev = None    # event: the last bookkeeping enqueued on the caller's stream (the LRU state prefetch builds on)
+        # merged step (bf16 AM / Arc): ONE statistics exchange per forward_pair instead of one per pass, the rollback pass's finalize
+        # reading through the overlay; rollback bookkeeping alternates between sets 0 and 2 so that the next step's (prefetch) never
+        # touches the set the current step still needs
+        self.merged = bool(getattr(self.backend, 'merged', False)) and not os.environ.get('FFC_DIST_NO_MERGE')
+        self._rb_set = 0
+        self._set_free = {}         # bookkeeping set -> event: the step that used it last has finished with it
+        self._route = None
+        if self.merged and self._nccl:
+            self._init_route(os.environ.get('FFC_DIST_NO_SYMM') is None)
+
+    def _init_route(self, try_symm):
+        """Staging for the reduce-scatter folded into finalize.  Preferred: a symmetric-memory buffer [R sources][2 passes][B][D] per
+        rank (torch.distributed._symmetric_memory: peer-mapped over NVLink, torch only provides the mapping and the barrier) -- every
+        rank's finalize kernels store the dLoss/dp rows of rank r's samples straight into r's buffer, one barrier, and r adds the R
+        slabs in rank order (ffc_sum_slabs: deterministic).  Fallback (no peer mapping): the same stores into a local
+        [R][2][B][D] buffer followed by ONE NCCL reduce-scatter per step."""
+        R, B, D, dev = self.R, self.B, self.D, self.dev
+        slab = 2 * B * D
+        self._route = dict(kind='nccl', slab=slab)
+        if try_symm:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                stage = symm_mem.empty(R * slab, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(stage, self.group if self.group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                assert len(ptrs) == R and ptrs[self.rank] == stage.data_ptr()
+                ok = torch.ones(1, device=dev)
+                self._route.update(kind='symm', stage=stage, hdl=hdl, ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev))
+            except Exception as e:      # noqa: BLE001 -- any failure of the optional peer mapping selects the NCCL route
+                ok = torch.zeros(1, device=dev)
+                self._route['symm_error'] = repr(e)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)     # all ranks take the same route
+            if float(ok) == 0.0:
+                self._route = dict(kind='nccl', slab=slab, symm_error=self._route.get('symm_error'))
+        if self._route['kind'] == 'nccl':
+            stage = torch.empty(R * slab, dtype=torch.float32, device=dev)
+            self._route.update(stage=stage, ptrs=torch.tensor([stage.data_ptr() + 4 * r * slab for r in range(R)], dtype=torch.int64, device=dev))
 
     # -- helpers ----------------------------------------------------------------------------------
     def shard_of(self, keys):
@@ -349,7 +426,7 @@ class ShardedFFCHead:
         self._discard_prefetch()
         if self._side is None:
             xl_all, yl_all = self._gather_labels(x_label, y_label)
-            ctx = self._bookkeep(xl_all, yl_all, False, 0)
+            ctx = self._bookkeep(xl_all, yl_all, False, self._next_rb_set())
             self._pre = dict(xl=xl_all, yl=yl_all, ctx=ctx, ev=None, src=(x_label, y_label))
             return
         main = torch.cuda.current_stream(self.dev)
@@ -359,12 +436,13 @@ class ShardedFFCHead:
                 ev_in = torch.cuda.Event()
                 ev_in.record(main)
                 self._side.wait_event(ev_in)
-            for e in (self._rb_done, self._lru_main_ev):
+            rb_set = self._next_rb_set()
+            for e in (self._set_free.get(rb_set) if self.merged else self._rb_done, self._lru_main_ev):
                 if e is not None:
                     self._side.wait_event(e)
             timing, self._timing = self._timing, None
             xl_all, yl_all = self._gather_labels(x_label, y_label, self._side_group)
-            ctx = self._bookkeep(xl_all, yl_all, False, 0, group=self._side_group)
+            ctx = self._bookkeep(xl_all, yl_all, False, rb_set, group=self._side_group)
             self._timing = timing
             ev = torch.cuda.Event()
             ev.record(self._side)
@@ -380,23 +458,28 @@ class ShardedFFCHead:
         labs = self._all_gather(own, group).view(R, 2 * B)
         return labs[:, :B].reshape(R * B), labs[:, B:].reshape(R * B)
 
+    def _next_rb_set(self):
+        """bookkeeping set of the NEXT rollback pass: merged steps alternate between 0 and 2, the per-pass flow always uses 0"""
+        return (2 - self._rb_set) if self.merged else 0
+
     def _discard_prefetch(self):
         pre, self._pre = self._pre, None
         if pre is None:
             return
-        # the LRU / queue positions were restored by the bookkeeping itself; only set 0's `ones` mask has to be cleared
+        # the LRU / queue positions were restored by the bookkeeping itself; only the set's `ones` mask has to be cleared
         be = self.backend
+        set_idx = pre['ctx']['set']
         if self._side is not None:
             with torch.cuda.stream(self._side):
                 if hasattr(be, 'use_set'):
-                    be.use_set(0)
+                    be.use_set(set_idx)
                 be.end_pass()
                 ev = torch.cuda.Event()
                 ev.record(self._side)
             torch.cuda.current_stream(self.dev).wait_event(ev)
         else:
             if hasattr(be, 'use_set'):
-                be.use_set(0)
+                be.use_set(set_idx)
             be.end_pass()
 
     def _take_prefetch(self, x_label, y_label):
@@ -428,7 +511,7 @@ class ShardedFFCHead:
             assert x_label is not None and y_label is not None, 'labels are required unless they were handed to prefetch()'
             x_all, xl_all, y_all, yl_all = self.gather_pair(x, y, x_label, y_label)
             self._mark('all_gather')
-            ctx_rb = self._bookkeep(xl_all, yl_all, False, 0)
+            ctx_rb = self._bookkeep(xl_all, yl_all, False, self._next_rb_set())
         else:
             x_all, _, y_all, _ = self.gather_pair(x, y)
             self._mark('all_gather')
@@ -439,6 +522,8 @@ class ShardedFFCHead:
                 for t in list(ctx_rb.values()) + [xl_all, yl_all]:
                     if torch.is_tensor(t):
                         t.record_stream(main)
+        if self.merged:
+            return self._forward_pair_merged(x_all, y_all, xl_all, yl_all, ctx_rb)
         if self._nccl and self._side is not None:
             # the commit pass's bookkeeping (LRU assign, probe labels) only needs the LRU state, which the rollback pass has
             # already restored: run it on a side stream underneath the rollback pass's sweep
@@ -462,6 +547,99 @@ class ShardedFFCHead:
             ctx_cm = self._bookkeep(yl_all, xl_all, True, 1)
         self._mark('start')
         l1, dy = self._finish(y_all, x_all, ctx_cm, True)
+        return l1 + l2, dx, dy
+
+    def _forward_pair_merged(self, x_all, y_all, xl_all, yl_all, ctx_rb):
+        """One step with ONE statistics exchange (bf16 AM / Arc):
+            enqueue_rb -> sweep_rb -> restore -> enqueue_cm -> sweep_cm -> all-gather of both passes' records -> finalize_rb (through the
+            overlay: its queue rows have been restored / re-enqueued since its sweep) -> finalize_cm -> dLoss/dp of both passes to their
+            owner ranks.
+        Three rendezvous per step ([x | y] all-gather, records, gradient rows) instead of five, the rank skew of two sweeps absorbed once;
+        the reduce-scatter is folded into finalize (peer stores + one barrier + a local fixed-order sum) when the ranks' staging buffers
+        are peer-mapped, and is one NCCL reduce-scatter per step otherwise."""
+        be, R, B, D = self.backend, self.R, self.B, self.D
+        n = x_all.shape[0]
+        rec = self._stats.get(('rec2', n))
+        if rec is None:
+            rec = self._stats[('rec2', n)] = be.new_records(n, R, passes=2)
+        rb_set = ctx_rb['set']
+        self._rb_set = rb_set
+        main = torch.cuda.current_stream(self.dev) if self._nccl else None
+        # commit pass's bookkeeping: on the side stream underneath the rollback sweep (it only needs the LRU, which the rollback
+        # bookkeeping has already restored)
+        if self._side is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                if self._set_free.get(1) is not None:
+                    self._side.wait_event(self._set_free[1])
+                timing, self._timing = self._timing, None
+                ctx_cm = self._bookkeep(yl_all, xl_all, True, 1)
+                self._timing = timing
+                ev_cm = torch.cuda.Event()
+                ev_cm.record(self._side)
+            for t in ctx_cm.values():
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+        else:
+            ctx_cm = None
+        # rollback pass: enqueue (+ overlay marks), sweep, restore
+        be.use_set(rb_set)
+        be.scatter(y_all, ctx_rb['order'], save_undo=True, overlay_table=0)
+        self._mark('scatter')
+        be.sweep_record(x_all, ctx_rb['label'], rec, 0)
+        self._mark('sweep')
+        be.restore_queue()
+        be.end_pass()
+        self._mark('restore')
+        # commit pass: enqueue (+ overlay marks, previous rows saved), sweep
+        if ctx_cm is None:
+            ctx_cm = self._bookkeep(yl_all, xl_all, True, 1)
+        else:
+            main.wait_event(ev_cm)
+        be.use_set(1)
+        be.scatter(x_all, ctx_cm['order'], save_undo=True, overlay_table=1)
+        self._mark('scatter')
+        be.sweep_record(y_all, ctx_cm['label'], rec, 1)
+        be.end_pass()
+        self._mark('sweep')
+        # the step's single statistics exchange
+        dist.all_gather_into_tensor(rec['all'].view(-1, rec['words']), rec['own'], group=self.group)
+        self._mark('stat_exchange')
+        route = self._route
+        if route is not None:
+            slab = route['slab']
+            base = self.rank * slab if route['kind'] == 'symm' else 0
+            r_rb, r_cm = (route['ptrs'], B, base), (route['ptrs'], B, base + B * D)
+        else:
+            r_rb = r_cm = None
+        be.use_set(rb_set)
+        l2, dx_part = be.finalize_gathered(x_all, ctx_rb['label'], rec, R, 0, overlay_g=y_all, route=r_rb)
+        be.use_set(1)
+        l1, dy_part = be.finalize_gathered(y_all, ctx_cm['label'], rec, R, 1, route=r_cm)
+        be.overlay_clear(rb_set)
+        be.overlay_clear(1)
+        self._mark('finalize')
+        if route is None:                              # CPU stand-in (gloo): plain sum of both passes' partial gradients
+            both = torch.stack([dx_part, dy_part])
+            dist.all_reduce(both, group=self.group)
+            sl = slice(self.rank * B, (self.rank + 1) * B)
+            dx, dy = both[0, sl].clone(), both[1, sl].clone()
+        else:
+            out = torch.empty(2, B, D, dtype=torch.float32, device=self.dev)
+            if route['kind'] == 'symm':
+                route['hdl'].barrier(channel=0)        # every rank's finalize stores have landed in this rank's staging buffer
+                be.sum_slabs(route['stage'], R, route['slab'], route['slab'], out)
+            else:
+                dist.reduce_scatter_tensor(out.view(-1), route['stage'], group=self.group)
+            dx, dy = out[0], out[1]
+        self._mark('reduce_scatter')
+        if self._side is not None:
+            for st_idx in (rb_set, 1):
+                self._set_free[st_idx] = torch.cuda.Event()
+                self._set_free[st_idx].record()
+        self._last = dict(label=ctx_cm['label'], n_mine=ctx_cm['n_mine'])
         return l1 + l2, dx, dy
 
     def _bookkeep(self, pl_all, gl_all, commit, set_idx, group=None):
@@ -507,7 +685,7 @@ class ShardedFFCHead:
                 rec = self._stats[('rec', n)] = be.new_records(n, R)
             be.sweep_record(p_all, label, rec)
             self._mark('sweep')
-            dist.all_gather_into_tensor(rec['all'], rec['own'], group=self.group)
+            dist.all_gather_into_tensor(rec['all'].view(-1, rec['words']), rec['own'], group=self.group)
             self._mark('stat_exchange')
             loss, dp_part = be.finalize_gathered(p_all, label, rec, R)
             self._mark('finalize')
@@ -554,6 +732,9 @@ class ShardedFFCHead:
         if self._side is not None and ctx['set'] == 0:
             self._rb_done = torch.cuda.Event()
             self._rb_done.record()
+        if self._side is not None and self.merged:      # a single pass between merged steps: its set is busy until here
+            self._set_free[ctx['set']] = torch.cuda.Event()
+            self._set_free[ctx['set']].record()
         self._mark('restore')
         self._last = dict(label=label, n_mine=ctx['n_mine'])
         return loss, dp
