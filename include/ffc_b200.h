@@ -139,6 +139,14 @@ int ffc_overlay_clear(int32_t* overlay_map_dev, const int32_t* rows_dev, const i
 /* out[e] = slabs[e] + slabs[slab_stride + e] + ... (n_slabs terms, in that order), e < n: the local half of the reduce-scatter
  * that ffc_head_finalize_gathered_ex starts with its peer stores.  n and slab_stride multiples of 4. */
 int ffc_sum_slabs(const float* slabs_dev, int n_slabs, int64_t slab_stride, int64_t n, float* out_dev, void* stream);
+/* ffc_sum_slabs behind a barrier across the ranks, in one launch (the second half of the reduce-scatter that the peers' finalize
+ * kernels started with their stores into this rank's staging buffer).  flag_ptrs_dev: device array of n_ranks pointers, entry r =
+ * rank r's flag words (int32[n_ranks], peer-mapped, zero before the first step); epoch: the step number, growing by one per call on
+ * every rank.  The kernel publishes `epoch` in every peer's flag word for this rank, waits until its own words have reached `epoch`,
+ * then sums.  *err_flag_dev is set to 1 if the wait exceeds 5 s (no hang; the sums are then meaningless). */
+int ffc_sum_slabs_barrier(const float* slabs_dev, int n_slabs, int64_t slab_stride, int64_t n, float* out_dev,
+                          int32_t* const* flag_ptrs_dev, int my_rank, int n_ranks, int32_t epoch, int32_t* err_flag_dev,
+                          void* stream);
 int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
                       const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
                       void* stream);

@@ -17,16 +17,17 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
+    routes = set()
     for precision, tol, D, Q, B, n_ids, loss_type, margin in (('bf16', 1e-2, 128, 1024, 96, 1500, 'Arc', 0.5),
                                                                ('fp32', 1e-5, 64, 512, 40, 700, 'AM', 0.4),
                                                                ('bf16', 1e-2, 512, 4096, 128, 4096, 'AM', 0.4),
+                                                               ('bf16', 1e-2, 128, 7409, 64, 9000, 'Arc', 0.5),      # ffc.py:11's default queue_size: uneven shards
                                                                ('bf16', 1e-2, 128, 1024, 96, 1500, 'SV', 0.4),
                                                                ('fp32', 1e-5, 64, 512, 40, 700, 'SV', 0.4)):
         torch.manual_seed(0)
         q0 = F.normalize(torch.rand(2, Q, D), dim=2)
         head = ShardedFFCHead(D, Q, 32.0, loss_type, margin, precision=precision, max_batch=B, device=dev)
-        Ql = Q // world
-        head.backend.set_queue(q0[:, rank * Ql:(rank + 1) * Ql])
+        head.backend.set_queue(q0[:, head.off:head.off + head.Ql])
         oracle = ShardedOracle(world, D, Q, 32.0, loss_type, margin, queue=q0, dtype=torch.float64)
         gen = torch.Generator().manual_seed(5)
         cen = F.normalize(torch.randn(n_ids, D, generator=gen))
@@ -72,12 +73,15 @@ def main():
             for got, want in ((xs.grad, xo.grad[sl]), (ys.grad, yo.grad[sl])):
                 err = float((got.double().cpu() - want).norm() / want.norm())
                 assert err <= tol, (precision, s, err)
+        if precision == 'bf16' and loss_type != 'SV':
+            assert head.merged and head._route is not None          # one exchange per step, reduce-scatter folded into finalize
+            routes.add(head._route['kind'])
         del head
     sharded_checkpoint_resume(rank, world, dev)
     long_run_odd_queue(rank, world, dev)
     dist.barrier()
     if rank == 0:
-        print('DIST_GPU_OK', world)
+        print('DIST_GPU_OK', world, 'routes', sorted(routes))
     dist.destroy_process_group()
 
 

@@ -30,7 +30,7 @@ def _batch(gen, B, D, n_ids):
 
 @pytest.mark.parametrize('D,Q,B,n_ids', [(512, 8192, 256, 9000), (128, 1000, 96, 3000)])
 def test_pass_single_is_sweep_plus_finalize(D, Q, B, n_ids):
-    """The fused reduce + coefficient + dEmb kernel sums in the same order as the three kernels it replaces: bit-identical."""
+    """The fused reduce + coefficient + dEmb kernel against the three kernels it replaces (same sums, fp32 instead of fp64 scalars)."""
     from ffc_b200 import _capi
     from ffc_b200._capi import HeadPass, HeadStats, check
     dev = torch.device('cuda')
@@ -58,8 +58,9 @@ def test_pass_single_is_sweep_plus_finalize(D, Q, B, n_ids):
         s = torch.cuda.current_stream().cuda_stream
         check(lib.ffc_head_sweep(h._h, C.byref(hp), C.byref(hs), s))
         check(lib.ffc_head_finalize(h._h, C.byref(hp), C.byref(hs), 1, loss2.data_ptr(), dp2.data_ptr(), s))
-        assert float(loss) == float(loss2), (step, float(loss), float(loss2))
-        assert torch.equal(dp, dp2), (step, _rel(dp, dp2))
+        # the fused kernel sums the partials in the same order; its per-row scalar part is fp32 (the three-kernel path: fp64)
+        assert abs(float(loss) - float(loss2)) <= 2e-6 * abs(float(loss2)), (step, float(loss), float(loss2))
+        assert _rel(dp, dp2) <= 2e-6, (step, _rel(dp, dp2))
 
 
 def test_forward_pair_equals_two_passes():

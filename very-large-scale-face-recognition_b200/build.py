@@ -52,5 +52,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_debug_lib() -> str:
+    """The bottleneck-isolation build of the sweep (-DFFC_SM100_DEBUG_BUILD=1: per-role cycle counters, switch-off modes) as a SEPARATE
+    library, build_dbg/libffc_b200_dbg.so; select it with FFC_B200_LIB=<path> (tools/sweep_modes.py).  Never the shipped library."""
+    out_dir = os.path.join(HERE, 'build_dbg')
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, 'libffc_b200_dbg.so')
+    objs = []
+    for src in _sources():
+        obj = os.path.join(out_dir, src[:-3] + '.o')
+        r = subprocess.run([NVCC] + FLAGS + ['-DFFC_SM100_DEBUG_BUILD=1', '-c', os.path.join(CSRC, src), '-o', obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{r.stdout}\n{r.stderr}')
+        objs.append(obj)
+    r = subprocess.run([NVCC, '-shared', '-o', lib] + objs + ['-cudart', 'static'], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    return lib
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--debug-lib' in sys.argv:
+        print(build_debug_lib())
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

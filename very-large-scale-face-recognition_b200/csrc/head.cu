@@ -752,7 +752,7 @@ constexpr int FR = 16;
 template <bool GATHERED>
 __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a, const float* __restrict__ rec,
                                                                   int64_t rec_stride) {
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int row0 = blockIdx.x * FR, n = a.n, D = a.D, k = a.k;
   __shared__ float s_l[FR][3];
   __shared__ float s_tv[FR][3][KMAX];
@@ -761,6 +761,7 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
   __shared__ int s_nw[FR];
   __shared__ int32_t s_wslot[FR][2 * KMAX];
   __shared__ uint8_t s_wrow[FR][2 * KMAX];
+  __shared__ WRow s_t0[FR], s_t1[FR];
   if (!GATHERED) {
     if (tid < FR * 3) {
       const int r = tid / 3, j = tid - 3 * r, i = row0 + r;
@@ -833,65 +834,91 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
     s_coef[r][3] = cT[1];
     s_nw[r] = nw;
   }
-  __syncthreads();
-  for (int r = w; r < FR; r += 4) {
-    const int i = row0 + r;
-    if (i >= n) break;
-    const bool outl = a.is_out[i];
-    const float cO0 = s_coef[r][0], cO1 = s_coef[r][1], cT0 = s_coef[r][2], cT1 = s_coef[r][3];
+  if (tid < FR && row0 + tid < n) {      // the rows' prototype rows (through the overlay), resolved once per row
+    const int i = row0 + tid;
     const int32_t tc = a.tcol[i];
-    const int nw = s_nw[r];
-    float* out = a.dp_peer ? a.dp_peer[i / a.dp_rows_per_rank] + a.dp_slot_off + (int64_t)(i % a.dp_rows_per_rank) * D : a.dp + (int64_t)i * D;
     WRow t0, t1;
     t0.h = t1.h = nullptr;
     t0.f = t1.f = nullptr;
-    if (!outl && tc >= 0) {
+    if (!a.is_out[i] && tc >= 0) {
       t0 = w_row(a, 0, tc);
       t1 = w_row(a, (a.tpos[i] >= 0) ? 1 : 0, tc);
     }
-    for (int d = lane * 4; d < D; d += 32 * 4) {
-      float g[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!outl) {
-        float o[3][4];
+    s_t0[tid] = t0;
+    s_t1[tid] = t1;
+  }
+  __syncthreads();
+  // phase 3: (row, 4 features) items dealt to the 128 threads; the chunk loads of an item are independent (issued four at a time,
+  // added in chunk order), so a thread keeps ~10 loads in flight -- with one warp per row and a serial chunk loop the kernel ran at
+  // memory LATENCY (70 us for 2 048 rows x 9 chunks: 37 MB)
+  const int D4 = D >> 2;
+  const int64_t cstride = (int64_t)n * D;
+  for (int item = tid; item < FR * D4; item += 128) {
+    const int r = item / D4, d = (item - r * D4) * 4;
+    const int i = row0 + r;
+    if (i >= n) break;
+    const bool outl = a.is_out[i];
+    float* out = a.dp_peer ? a.dp_peer[i / a.dp_rows_per_rank] + a.dp_slot_off + (int64_t)(i % a.dp_rows_per_rank) * D : a.dp + (int64_t)i * D;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!outl) {
+      const float cO0 = s_coef[r][0], cO1 = s_coef[r][1], cT0 = s_coef[r][2], cT1 = s_coef[r][3];
+      float o[3][4];
 #pragma unroll
-        for (int jb = 0; jb < 3; ++jb) {
-          const ReduceJob& rj = jobs.j[jb];
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int c = 0; c < rj.n_chunks; ++c) {
-            const float4 v = __ldcs(reinterpret_cast<const float4*>(rj.o_part + ((int64_t)c * n + i) * D + d));
-            acc.x += v.x;
-            acc.y += v.y;
-            acc.z += v.z;
-            acc.w += v.w;
-          }
-          o[jb][0] = acc.x;
-          o[jb][1] = acc.y;
-          o[jb][2] = acc.z;
-          o[jb][3] = acc.w;
-        }
+      for (int jb = 0; jb < 3; ++jb) {
+        const ReduceJob& rj = jobs.j[jb];
+        const float* base = rj.o_part + (int64_t)i * D + d;
+        const int nc = rj.n_chunks;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = 0;
+        for (; c + 4 <= nc; c += 4) {
+          float4 v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) g[e] = cO0 * (o[0][e] + o[1][e]) + cO1 * (o[0][e] + o[2][e]);
-        if (tc >= 0) {
-          const float4 w0 = w_load4(t0, d), w1 = w_load4(t1, d);
-          g[0] += cT0 * w0.x + cT1 * w1.x;
-          g[1] += cT0 * w0.y + cT1 * w1.y;
-          g[2] += cT0 * w0.z + cT1 * w1.z;
-          g[3] += cT0 * w0.w + cT1 * w1.w;
-        }
-      } else {
-        for (int x = 0; x < nw; ++x) {
-          const int64_t loc = (int64_t)s_wslot[r][x] - a.col_offset;
-          if (loc >= 0 && loc < a.q_local) {
-            const float4 wv = w_load4(w_row(a, s_wrow[r][x], loc), d);
-            g[0] += cO0 * wv.x;
-            g[1] += cO0 * wv.y;
-            g[2] += cO0 * wv.z;
-            g[3] += cO0 * wv.w;
+          for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(base + (c + u) * cstride));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc.x += v[u].x;
+            acc.y += v[u].y;
+            acc.z += v[u].z;
+            acc.w += v[u].w;
           }
+        }
+        for (; c < nc; ++c) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(base + c * cstride));
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+        o[jb][0] = acc.x;
+        o[jb][1] = acc.y;
+        o[jb][2] = acc.z;
+        o[jb][3] = acc.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) g[e] = cO0 * (o[0][e] + o[1][e]) + cO1 * (o[0][e] + o[2][e]);
+      const WRow t0 = s_t0[r], t1 = s_t1[r];
+      if (t0.h) {
+        const float4 w0 = w_load4(t0, d), w1 = w_load4(t1, d);
+        g[0] += cT0 * w0.x + cT1 * w1.x;
+        g[1] += cT0 * w0.y + cT1 * w1.y;
+        g[2] += cT0 * w0.z + cT1 * w1.z;
+        g[3] += cT0 * w0.w + cT1 * w1.w;
+      }
+    } else {
+      const float cO0 = s_coef[r][0];
+      const int nw = s_nw[r];
+      for (int x = 0; x < nw; ++x) {
+        const int64_t loc = (int64_t)s_wslot[r][x] - a.col_offset;
+        if (loc >= 0 && loc < a.q_local) {
+          const float4 wv = w_load4(w_row(a, s_wrow[r][x], loc), d);
+          g[0] += cO0 * wv.x;
+          g[1] += cO0 * wv.y;
+          g[2] += cO0 * wv.z;
+          g[3] += cO0 * wv.w;
         }
       }
-      *reinterpret_cast<float4*>(out + d) = make_float4(g[0], g[1], g[2], g[3]);
     }
+    *reinterpret_cast<float4*>(out + d) = make_float4(g[0], g[1], g[2], g[3]);
   }
 }
 

@@ -203,7 +203,64 @@ __global__ void __launch_bounds__(256) sum_slabs_kernel(const float4* __restrict
     out[i] = acc;
   }
 }
+// The same sum behind a barrier across the ranks, in ONE launch: the slabs are written by the PEERS' finalize kernels (stores over
+// NVLink into this rank's peer-mapped staging buffer).  Block 0 tells every peer "my stores of step `epoch` are out" (the finalize
+// kernels that issued them precede this launch in stream order; a system-scope fence, then a release store of the step number into
+// the peer's flag word), every block waits until all peers have said so for this rank (acquire loads of its own flag words), then
+// sums.  The flag words only ever grow, so a peer that is already a step ahead releases the wait as well.  A wait that lasts longer
+// than `timeout_ns` raises *err_flag and goes on (wrong sums, no hang).
+__global__ void __launch_bounds__(256) sum_slabs_barrier_kernel(const float4* __restrict__ slabs, int n_slabs, int64_t stride4, int64_t n4,
+                                                                float4* __restrict__ out, int32_t* const* __restrict__ flag_ptrs, int my_rank,
+                                                                int n_ranks, int32_t epoch, int32_t* err_flag, long long timeout_ns) {
+  if (blockIdx.x == 0 && threadIdx.x < n_ranks) {
+    __threadfence_system();
+    int32_t* dst = flag_ptrs[threadIdx.x] + my_rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x < n_ranks) {
+    const int32_t* src = flag_ptrs[my_rank] + threadIdx.x;
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+      int32_t v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if (v - epoch >= 0) break;
+      long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        *err_flag = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = __ldcs(slabs + i);
+    for (int r = 1; r < n_slabs; ++r) {
+      const float4 v = __ldcs(slabs + r * stride4 + i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    out[i] = acc;
+  }
+}
 }  // namespace ffc
+
+extern "C" int ffc_sum_slabs_barrier(const float* slabs_dev, int n_slabs, int64_t slab_stride, int64_t n, float* out_dev, int32_t* const* flag_ptrs_dev,
+                                     int my_rank, int n_ranks, int32_t epoch, int32_t* err_flag_dev, void* stream) {
+  FFC_REQUIRE(slabs_dev && out_dev && flag_ptrs_dev && err_flag_dev && n_slabs >= 1 && n >= 0 && n % 4 == 0 && slab_stride % 4 == 0,
+              "ffc_sum_slabs_barrier: bad arguments (n and the stride must be multiples of 4)");
+  FFC_REQUIRE(n_ranks >= 1 && n_ranks <= 64 && my_rank >= 0 && my_rank < n_ranks, "ffc_sum_slabs_barrier: rank %d of %d", my_rank, n_ranks);
+  // at most one resident wave of blocks: a block that is not resident cannot keep a peer waiting, but there is no point in more
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n / 4, 256), 148 * 4));
+  sum_slabs_barrier_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)slabs_dev, n_slabs, slab_stride / 4, n / 4, (float4*)out_dev, flag_ptrs_dev,
+                                                                      my_rank, n_ranks, epoch, err_flag_dev, 5000000000LL);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
 
 extern "C" int ffc_overlay_clear(int32_t* overlay_map_dev, const int32_t* rows_dev, const int32_t* cols_dev, int n, int64_t Q, void* stream) {
   FFC_REQUIRE(overlay_map_dev && rows_dev && cols_dev && n >= 0 && Q >= 1, "ffc_overlay_clear: bad arguments");

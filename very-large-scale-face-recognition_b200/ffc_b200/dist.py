@@ -196,8 +196,15 @@ class CudaShardBackend:
                                                      w * passes, C.byref(opts), loss.data_ptr(), None if dp is None else dp.data_ptr(), self._s()))
         return loss, dp
 
-    def sum_slabs(self, slabs, n_slabs, stride, n, out):
-        check(self.lib.ffc_sum_slabs(slabs.data_ptr(), n_slabs, stride, n, out.data_ptr(), self._s()))
+    def sum_slabs(self, slabs, n_slabs, stride, n, out, barrier=None):
+        """out = sum of the slabs in order; barrier = (flag pointer table, rank, ranks, epoch, error flag): first meet the peers whose
+        finalize kernels wrote the slabs (one launch)"""
+        if barrier is None:
+            check(self.lib.ffc_sum_slabs(slabs.data_ptr(), n_slabs, stride, n, out.data_ptr(), self._s()))
+        else:
+            fp, rank, ranks, epoch, err = barrier
+            check(self.lib.ffc_sum_slabs_barrier(slabs.data_ptr(), n_slabs, stride, n, out.data_ptr(), fp.data_ptr(), rank, ranks, epoch & 0x7fffffff,
+                                                 err.data_ptr(), self._s()))
 
     def sweep(self, p_all, label, st, rank_slot):
         hp, hs = self._structs(p_all, label, st, rank_slot)
@@ -319,12 +326,15 @@ class ShardedFFCHead:
         if try_symm:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                stage = symm_mem.empty(R * slab, dtype=torch.float32, device=dev)
+                stage = symm_mem.empty(R * slab + 64, dtype=torch.float32, device=dev)          # + the barrier's flag words (int32[R])
                 hdl = symm_mem.rendezvous(stage, self.group if self.group is not None else dist.group.WORLD)
                 ptrs = [int(p) for p in hdl.buffer_ptrs]
-                assert len(ptrs) == R and ptrs[self.rank] == stage.data_ptr()
+                assert len(ptrs) == R and ptrs[self.rank] == stage.data_ptr() and R <= 64
+                stage.zero_()
                 ok = torch.ones(1, device=dev)
-                self._route.update(kind='symm', stage=stage, hdl=hdl, ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev))
+                self._route.update(kind='symm', stage=stage, hdl=hdl, ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
+                                   flags=torch.tensor([p + 4 * R * slab for p in ptrs], dtype=torch.int64, device=dev),
+                                   err=torch.zeros(1, dtype=torch.int32, device=dev), epoch=0)
             except Exception as e:      # noqa: BLE001 -- any failure of the optional peer mapping selects the NCCL route
                 ok = torch.zeros(1, device=dev)
                 self._route['symm_error'] = repr(e)
@@ -629,8 +639,10 @@ class ShardedFFCHead:
         else:
             out = torch.empty(2, B, D, dtype=torch.float32, device=self.dev)
             if route['kind'] == 'symm':
-                route['hdl'].barrier(channel=0)        # every rank's finalize stores have landed in this rank's staging buffer
-                be.sum_slabs(route['stage'], R, route['slab'], route['slab'], out)
+                # one launch: meet the peers (their finalize stores have landed in this rank's staging buffer), then add the R slabs
+                route['epoch'] += 1
+                be.sum_slabs(route['stage'], R, route['slab'], route['slab'], out,
+                             barrier=(route['flags'], self.rank, R, route['epoch'], route['err']))
             else:
                 dist.reduce_scatter_tensor(out.view(-1), route['stage'], group=self.group)
             dx, dy = out[0], out[1]
