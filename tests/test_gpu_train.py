@@ -88,6 +88,19 @@ def test_drop_in_for_the_reference_module_with_its_own_backbones(net_type, D, B,
     keep the test short).  Identities are drawn from a pool of 3 x batch so that hits, `ones`, misses and outliers all occur."""
     if REF not in sys.path:
         sys.path.insert(0, REF)
+    if net_type == 'mobile':
+        # On this image (torch 2.11 + its cuDNN, B200) the reference's MobileFaceNet -- alone, without any code of this repo --
+        # returns NaN from its second forward on once a backward has produced non-finite gradients, which fp16 autocast with a
+        # GradScaler-sized factor does on the first steps (tools/debug_mobile4.py: reference FFC / bare backbone, cuDNN on -> NaN,
+        # cuDNN off -> finite).  The backbones are outside the hot path; the comparison runs them on the native kernels.
+        ctx = torch.backends.cudnn.flags(enabled=False)
+    else:
+        ctx = contextlib.nullcontext()
+    with ctx:
+        _drop_in(net_type, D, B, Q, steps)
+
+
+def _drop_in(net_type, D, B, Q, steps):
     import ffc as ref_ffc                                  # the unmodified reference module (oracle/_ref or /root/reference)
     import ffc_b200
     assert os.path.realpath(ref_ffc.__file__).startswith(os.path.realpath(REF))
@@ -141,6 +154,7 @@ def test_train_one_epoch_with_the_reference_mobilefacenet():
     scaler = torch.amp.GradScaler('cuda')
     src = T.SyntheticSource(num_class=10000, batch_size=64, image_size=112, batches_per_epoch=8, seed=3)
     logs = []
-    n = T.train_one_epoch(src.id_loader(), src.instance_loader(), net, opt, scaler, save_every=2, device=dev, log=logs.append)
+    with torch.backends.cudnn.flags(enabled=False):        # see test_drop_in_...: the reference backbone's cuDNN path turns NaN on this image
+        n = T.train_one_epoch(src.id_loader(), src.instance_loader(), net, opt, scaler, save_every=2, device=dev, log=logs.append)
     assert n == 8 and len(logs) == 4 and all(np.isfinite(l['loss']) for l in logs), logs
     assert net.prefetch_hits == 7 and net.lru.cur_idx > 64

@@ -738,7 +738,8 @@ __device__ __forceinline__ float4 w_load4(const WRow& w, int d) {
 }
 
 // Fast path of the bf16 AM / Arc head: chunk reduction of the three sweeps' partials, the scalar part and dLoss/dp in ONE
-// launch.  No osum round trip through HBM; replaces reduce + row_coef + finalize.  A block takes FR = 16 rows:
+// launch.  No osum round trip through HBM; replaces reduce + row_coef + finalize.  A block takes FR = 4 rows (2 048 blocks at the 8-GPU
+// row count: the partial sums are ~100 MB to read, and it takes that many loads in flight to read them at the HBM rate):
 //   phase 1 (GATHERED = false only): one thread per (row, sweep) sums the chunk denominators and merges the chunk top-k lists;
 //   phase 2: one THREAD per row does the scalar part (margin function, log / exp, top-k merge over ranks) -- in fp32, all rows of
 //            the grid side by side (one lane per row on the fp64 pipe cost 16 us per row, 3.5 waves of it at 8 192 rows);
@@ -748,7 +749,7 @@ __device__ __forceinline__ float4 w_load4(const WRow& w, int d) {
 //   GATHERED = true (sharded head): the scalars come from the n_ranks gathered records (`rec`, `rec_stride` words apart),
 //     summed in rank order on every rank; O is this rank's partial, so dp is this rank's contribution -- stored locally for a
 //     reduce-scatter, or (dp_peer) straight into the owner rank's staging buffer.
-constexpr int FR = 16;
+constexpr int FR = 4;
 template <bool GATHERED>
 __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJobs jobs, const FinalizeArgs a, const float* __restrict__ rec,
                                                                   int64_t rec_stride) {
@@ -848,9 +849,9 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
     s_t1[tid] = t1;
   }
   __syncthreads();
-  // phase 3: (row, 4 features) items dealt to the 128 threads; the chunk loads of an item are independent (issued four at a time,
-  // added in chunk order), so a thread keeps ~10 loads in flight -- with one warp per row and a serial chunk loop the kernel ran at
-  // memory LATENCY (70 us for 2 048 rows x 9 chunks: 37 MB)
+  // phase 3: (row, 4 features) items dealt to the 128 threads; the chunk loads of an item are independent (issued eight at a time,
+  // added in chunk order) -- with one warp per row and a serial chunk loop the kernel ran at memory LATENCY (70 us for 2 048 rows x
+  // 9 chunks: 37 MB)
   const int D4 = D >> 2;
   const int64_t cstride = (int64_t)n * D;
   for (int item = tid; item < FR * D4; item += 128) {
@@ -870,17 +871,29 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
         const int nc = rj.n_chunks;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int c = 0;
-        for (; c + 4 <= nc; c += 4) {
-          float4 v[4];
+        for (; c + 8 <= nc; c += 8) {
+          float4 v[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(base + (c + u) * cstride));
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(base + (c + u) * cstride));
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             acc.x += v[u].x;
             acc.y += v[u].y;
             acc.z += v[u].z;
             acc.w += v[u].w;
           }
+        }
+        for (; c + 2 <= nc; c += 2) {
+          const float4 v0 = __ldcs(reinterpret_cast<const float4*>(base + c * cstride));
+          const float4 v1 = __ldcs(reinterpret_cast<const float4*>(base + (c + 1) * cstride));
+          acc.x += v0.x;
+          acc.y += v0.y;
+          acc.z += v0.z;
+          acc.w += v0.w;
+          acc.x += v1.x;
+          acc.y += v1.y;
+          acc.z += v1.z;
+          acc.w += v1.w;
         }
         for (; c < nc; ++c) {
           const float4 v = __ldcs(reinterpret_cast<const float4*>(base + c * cstride));

@@ -396,6 +396,18 @@ class ShardedFFCHead:
         l_all = self._all_gather(torch.as_tensor(label).to(device=dev, dtype=torch.int64))
         return e_all, l_all
 
+    def staging(self):
+        """The rank's slice of the packed all-gather input, as two fp32 [B, D] views (x, y).  Hand them to the backbone tail
+        (``FFCTail(...)(feat, out=view)`` / ``l2_normalize(feat, out=view)``, csrc/tail.cu) and pass the results to
+        :meth:`forward_pair`: the unit-norm rows are then written ONCE, where the exchange reads them (SURVEY 8(f) rank 3's
+        "all-gather staging"); any other tensors are copied in.  The views stay valid for the life of the head; a step's rows must
+        be written after the previous forward_pair call has returned."""
+        if getattr(self, '_own', None) is None:
+            ne = self.B * self.D
+            self._own = torch.empty(2 * ne + 4 * self.B, dtype=torch.float32, device=self.dev)      # [x | y | x_label, y_label (int64)]
+        ne = self.B * self.D
+        return self._own[:ne].view(self.B, self.D), self._own[ne:2 * ne].view(self.B, self.D)
+
     def gather_pair(self, x, y, x_label=None, y_label=None):
         """Both sides of the batch in ONE all-gather (NCCL): each rank contributes [x | y | x_label | y_label] as one packed
         buffer of 4-byte words.  Returns (x_all, xl_all, y_all, yl_all) in global batch order (rank-major); without labels
@@ -409,9 +421,13 @@ class ShardedFFCHead:
         dev, B, D, R = self.dev, self.B, self.D, self.R
         assert x.shape == (B, D) and y.shape == (B, D), f'every rank must feed max_batch={B} rows of {D} features'
         ne = B * D
-        own = torch.empty(2 * ne + (4 * B if with_labels else 0), dtype=torch.float32, device=dev)
-        own[:ne].view(B, D).copy_(x.detach())
-        own[ne:2 * ne].view(B, D).copy_(y.detach())
+        sx, sy = self.staging()
+        own = self._own if with_labels else self._own[:2 * ne]
+        # rows the backbone tail already wrote into the staging views (FFCTail / l2_normalize `out=`) are not copied again
+        if not (x.data_ptr() == sx.data_ptr() and x.is_contiguous() and x.dtype == torch.float32):
+            sx.copy_(x.detach())
+        if not (y.data_ptr() == sy.data_ptr() and y.is_contiguous() and y.dtype == torch.float32):
+            sy.copy_(y.detach())
         if with_labels:
             lab = own[2 * ne:].view(torch.int64)
             lab[:B].copy_(torch.as_tensor(x_label).reshape(B), non_blocking=True)
