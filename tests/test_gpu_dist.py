@@ -20,4 +20,9 @@ def test_sharded_head_nccl(world):
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'dist_gpu_worker.py')
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
                         '--master-port', str(port), worker], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and 'DIST_GPU_OK' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    if r.returncode != 0:       # keep the whole worker log (the first failing rank's message scrolls out of a tail)
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, f'dist_worker_world{world}.log'), 'w') as f:
+                f.write(r.stdout + '\n---- stderr ----\n' + r.stderr)
+    assert r.returncode == 0 and 'DIST_GPU_OK' in r.stdout, '\n'.join(l for l in (r.stdout + r.stderr).splitlines() if 'rank' in l and 'File' not in l)[-4000:]

@@ -34,7 +34,7 @@ for trial in range(3):
     p = F.normalize(torch.randn(n, D, generator=gen)).to(dev)
     label = torch.randint(0, Q, (n,), generator=gen).to(torch.int32)
     label[torch.rand(n, generator=gen) < 0.4] = -1
-    ones_global = torch.randperm(Q, generator=gen)[:24].sort().values
+    ones_global = torch.randperm(Q, generator=gen)[:int(os.environ.get('REPRO_ONES', 24))].sort().values
     label[:6] = ones_global[:6].to(torch.int32)
     label = label.to(dev)
 
@@ -69,4 +69,49 @@ for trial in range(3):
         dp_sum += dp
     row_err = (dp_sum - dp_ref).norm(dim=1) / (dp_ref.norm(dim=1) + 1e-30)
     bad = torch.nonzero(row_err > 1e-3).flatten().tolist()
+    if bad:
+        # per-rank record candidates of the first bad row against a torch recomputation
+        b = bad[0]
+        k = hard_neg_k(Q)
+        pb = p[b].to(torch.bfloat16).float()
+        for r, be in enumerate(shards):
+            w = recs[r]['words']
+            rec = recs[r]['own'][0]
+            topv = rec[8 * n:8 * n + 3 * n * k].view(3, n, k)[:, b]
+            topi = rec[8 * n + 3 * n * k:].view(torch.int32).view(3, n, k)[:, b]
+            n1 = int(be.n_ones)
+            ol = be.ones_list[:n1].long()
+            c0 = be.queue_bf16[0].float() @ pb
+            c1 = be.queue_bf16[1].float() @ pb
+            cm = c0.clone(); cm[ol] = -9
+            print(f'  row {b} rank {r}: record common {topv[0].tolist()} {topi[0].tolist()} | torch {torch.topk(cm, k).values.tolist()} {(torch.topk(cm, k).indices + r * Ql).tolist()}')
+            for l, cc in ((1, c0), (2, c1)):
+                tv = torch.topk(cc[ol], min(k, n1))
+                print(f'           side{l - 1} record {topv[l].tolist()} {topi[l].tolist()} | torch {tv.values.tolist()} {(ol[tv.indices] + r * Ql).tolist()} (n_ones {n1})')
+    # every outlier row's recorded candidates against a torch top-k over the same bf16 operands
+    k = hard_neg_k(Q)
+    p16 = p.to(torch.bfloat16).float()
+    n_mis = 0
+    for r, be in enumerate(shards):
+        rec = recs[r]['own'][0]
+        topv = rec[8 * n:8 * n + 3 * n * k].view(3, n, k)
+        n1 = int(be.n_ones)
+        ol = be.ones_list[:n1].long()
+        c0 = p16 @ be.queue_bf16[0].float().t()
+        c1 = p16 @ be.queue_bf16[1].float().t()
+        cm = c0.clone()
+        cm[:, ol] = -9.0
+        want = [torch.topk(cm, k, dim=1).values, torch.topk(c0[:, ol], min(k, n1), dim=1).values, torch.topk(c1[:, ol], min(k, n1), dim=1).values]
+        outl = (label < 0)
+        for sidx in range(3):
+            got = topv[sidx][outl][:, :want[sidx].shape[1]]
+            w_ = want[sidx][outl].clamp_min(0)          # only positive cosines are kept (the rest cannot contribute)
+            g_ = torch.where(torch.isinf(got), torch.zeros_like(got), got).clamp_min(0)
+            d = (g_ - w_).abs().max(dim=1).values
+            badr = torch.nonzero(d > 2e-3).flatten()
+            n_mis += int(badr.numel())
+            if badr.numel():
+                i = int(badr[0])
+                print(f'  rank {r} set {sidx}: {int(badr.numel())} outlier rows differ; first: got {g_[i].tolist()} want {w_[i].tolist()} (n_ones {n1})')
+    print(f'  top-k candidate mismatches vs torch: {n_mis}')
     print(f'trial {trial}: loss {losses} vs {float(loss_ref):.6f}; max row err {float(row_err.max()):.3e}; bad rows {bad[:10]} labels {[int(label[b]) for b in bad[:10]]}', flush=True)
