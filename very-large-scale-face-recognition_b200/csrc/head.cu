@@ -933,6 +933,9 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
     }
     *reinterpret_cast<float4*>(out + d) = make_float4(g[0], g[1], g[2], g[3]);
   }
+  // rows stored into a peer's staging buffer: make them visible system-wide before this kernel counts as finished -- the flag that
+  // tells the peer "my rows are there" is written by the next launch in the stream (ffc_sum_slabs_barrier)
+  if (a.dp_peer) __threadfence_system();
 }
 
 // Pass 2, one block per row: dLoss/dp from the accumulated sums (bandwidth bound).

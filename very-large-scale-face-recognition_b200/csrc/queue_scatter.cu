@@ -235,10 +235,11 @@ __global__ void __launch_bounds__(256) sum_slabs_barrier_kernel(const float4* __
     }
   }
   __syncthreads();
+  // the slabs were written by other GPUs: read them at the L2 (the point of coherence for peer stores), never from a stale L1 line
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 acc = __ldcs(slabs + i);
+    float4 acc = __ldcg(slabs + i);
     for (int r = 1; r < n_slabs; ++r) {
-      const float4 v = __ldcs(slabs + r * stride4 + i);
+      const float4 v = __ldcg(slabs + r * stride4 + i);
       acc.x += v.x;
       acc.y += v.y;
       acc.z += v.z;
