@@ -150,6 +150,13 @@ int ffc_sum_slabs_barrier(const float* slabs_dev, int n_slabs, int64_t slab_stri
 int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
                       const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
                       void* stream);
+/* ffc_queue_restore for a PACKED list: the live positions (cols >= 0) come first, everything after the first padded position is
+ * padded too -- what ffc_route_keys + ffc_lru_assign(n_dev) produce for a rank of the sharded head (its own keys compacted to the
+ * front of the R*B gathered positions).  The duplicate scans stop at the first padded position.  ffc_queue_scatter_indexed /
+ * ffc_queue_scatter_overlay make the same assumption about their lists. */
+int ffc_queue_restore_packed(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev,
+                             const int32_t* cols_dev, const float* undo_f32_dev, int B, int64_t Q, int D,
+                             void* stream);
 /* ------------------------------------------------------------------------------------------------
  * Gallery-network EMA (replaces ffc.py:139-145 _momentum_update_gallery), SURVEY 8(f) rank 1.
  * One launch over all parameter tensors: the caller splits every fp32 tensor into chunks of at most

@@ -128,7 +128,7 @@ def main():
                         assert min(gaps) < 3e-3, (precision, D, Q, loss_type, s, name, 'outlier row off without a near-tie', b, gaps, 'rows off', int((row_err > 10 * tol).sum()))
                         skip[b] = True
                 err = float((got[~skip] - want[~skip]).norm() / want[~skip].norm())
-                assert err <= tol and int(skip.sum()) <= 3, (precision, s, name, err, int(skip.sum()))
+                assert err <= tol and int(skip.sum()) <= max(3, B // 16), (precision, s, name, err, int(skip.sum()))
         if precision == 'bf16' and loss_type != 'SV':
             assert os.environ.get('FFC_DIST_NO_MERGE') or (head.merged and head._route is not None)   # one exchange per step, reduce-scatter folded into finalize
             routes.add(head._route['kind'] if head._route else 'per-pass')

@@ -17,9 +17,11 @@ pk = json.load(open(os.path.join(R, 'MEASURED_PEAKS.json'))) if os.path.isfile(o
 B, steps, warm = 1024, 8, 2
 print('| D | queue | loss | sweep ms | TFLOP/s (4BQD) | of burst bf16 peak | step ms (2 passes) | samples/s |')
 print('|---:|---:|---|---:|---:|---:|---:|---:|')
-for D in (128, 256, 512):
-    for Q in (16384, 65536, 262144, 1048576, 2097152):
-        for loss_type, margin in (('Arc', 0.5), ('AM', 0.4)):
+DS = [int(v) for v in os.environ.get('C5_D', '128,256,512').split(',')]
+QS = [int(v) for v in os.environ.get('C5_Q', '16384,65536,262144,1048576,2097152').split(',')]
+for D in DS:
+    for Q in QS:
+        for loss_type, margin in ((('Arc', 0.5), ('AM', 0.4)) if not os.environ.get('C5_ARC_ONLY') else (('Arc', 0.5),)):
             torch.manual_seed(0)
             h = ffc_b200.FFCHead(D, Q, 32.0, loss_type, margin, precision='bf16', max_batch=B, device=dev)
             h._ensure()

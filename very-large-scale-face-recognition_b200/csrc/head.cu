@@ -794,11 +794,55 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
     }
     __syncthreads();
   }
+  // GATHERED: the ranks' records are staged through shared memory by all threads -- per row 6 scalars x R ranks and, for an outlier
+  // row, 3 candidate sets x R ranks x k (value, slot) pairs.  Read by the one thread that does the row's scalar part they were
+  // ~50 (positive row) / ~500 (outlier row) dependent global loads: the latency of this phase paced the kernel at 8 ranks.
+  constexpr int RS = 16;                       // ranks the staging is sized for (more: the records are read in place)
+  __shared__ float s_red[GATHERED ? FR : 1][6][GATHERED ? RS : 1];
+  __shared__ float s_cv[GATHERED ? FR : 1][3][GATHERED ? RS : 1][KMAX];
+  __shared__ int32_t s_ci[GATHERED ? FR : 1][3][GATHERED ? RS : 1][KMAX];
+  const bool staged = GATHERED && a.n_ranks <= RS;
+  if (staged) {
+    const int R = a.n_ranks;
+    for (int e = tid; e < FR * 6 * R; e += 128) {
+      const int r = e / (6 * R), j = (e / R) % 6, q = e % R, i = row0 + r;
+      if (i < n) s_red[r][j][q] = rec[q * rec_stride + (int64_t)j * n + i];
+    }
+    for (int e = tid; e < FR * 3 * R * k; e += 128) {
+      const int r = e / (3 * R * k), set = (e / (R * k)) % 3, q = (e / k) % R, x = e % k, i = row0 + r;
+      if (i < n && a.is_out[i]) {
+        const float* base = rec + q * rec_stride + 8 * (int64_t)n;
+        const int64_t o = ((int64_t)set * n + i) * k + x;
+        s_cv[r][set][q][x] = base[o];
+        s_ci[r][set][q][x] = reinterpret_cast<const int32_t*>(base + 3 * (int64_t)n * k)[o];
+      }
+    }
+    __syncthreads();
+  }
   if (tid < FR && row0 + tid < n) {
     const int r = tid, i = row0 + r;
     float loss, cO[2], cT[2];
     int nw;
-    if (GATHERED) {
+    if (staged) {
+      const int R = a.n_ranks;
+      row_coef_math<float>(
+          a, i, R,
+          [&](int slot) {
+            float acc = 0.f;
+            for (int q = 0; q < R; ++q) acc += s_red[r][slot][q];      // rank order: the same sum on every rank
+            return acc;
+          },
+          [&](int l) {
+            float acc = 0.f;
+            for (int q = 0; q < R; ++q) acc += s_red[r][4 + l][q];
+            return acc;
+          },
+          [&](int q, int set, int e, float& v, int32_t& idx) {
+            v = s_cv[r][set][q][e];
+            idx = s_ci[r][set][q][e];
+          },
+          loss, cO, cT, nw, s_wslot[r], s_wrow[r]);
+    } else if (GATHERED) {
       const int R = a.n_ranks;
       row_coef_math<float>(
           a, i, R,

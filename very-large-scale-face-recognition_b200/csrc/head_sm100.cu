@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "head_internal.cuh"
+#include "sm100_ptx.cuh"
 
 namespace ffc {
 
@@ -51,7 +52,6 @@ constexpr int JB = FFC_JB;         // queue rows per O-CTA W stage
 constexpr int NEPI = 3;             // epilogue warpgroups in the S-CTA (tiles are dealt round-robin)
 constexpr int NTHREADS = 128 + NEPI * 128;   // 4 control warps + 12 epilogue warps
 constexpr int CHUNK1_BYTES = BN * KC * 2;   // 16384
-constexpr float LOG2E = 1.4426950408889634f;
 
 // ---- shared memory map (same for both roles; 1024-byte aligned base) ----
 // [0, 1024)                 barriers, tmem base
@@ -79,240 +79,11 @@ struct Bars {   // all in the first 1024 bytes
 };
 static_assert(sizeof(Bars) <= 1024, "barrier block too large");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(addr),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // pairs with a remote release.cluster arrive
-  const uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAITC_DONE;\n"
-      "bra WAITC_LOOP;\n"
-      "WAITC_DONE:\n"
-      "}\n" ::"r"(addr),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y, int z) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
-      "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
-      "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-        "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// asynchronous 16-byte store into the peer CTA's shared memory; completion is counted (complete_tx) on the
-// peer's mbarrier, so the writer needs no fence / drain before the consumer may be released
-__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(a), "r"(b),
-               "r"(c), "r"(d), "r"(mbar)
-               : "memory");
-}
-// tcgen05.commit that arrives on the barrier at the same offset in the CTAs of `cta_mask`
-__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-
-// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): SWIZZLE_128B, version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
-  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 0 = SWIZZLE_NONE (interleaved 8x16-byte core matrices)
-  return d;
-}
-// instruction descriptor (InstrDescriptor): bf16 x bf16 -> f32
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
 // Byte offset of the 16-byte piece `piece` (= 8 consecutive queue columns, 0..15) of row `r` inside one 32 KB P~ buffer:
 // the interleaved (SWIZZLE_NONE) K-major layout, 8x16-byte core matrices with the 128 rows of one piece contiguous
 // (2 KB).  The 32 lanes of a warp (32 consecutive rows) therefore write 512 contiguous bytes per store instruction --
 // coalesced DSMEM traffic (hand-off alone: 0.80 ms per sweep, against 1.47 ms for 128-byte-strided SWIZZLE_128B rows).
 __device__ __forceinline__ uint32_t pt_offset(uint32_t piece, uint32_t r) { return piece * (uint32_t)(BM * 16) + r * 16u; }
-
-// One lane of a converged warp; the warp stays converged, so descriptors live in uniform registers and consecutive
-// tcgen05.mma issue back to back.  (Issuing from an `if (lane == 0)` region makes every MMA pay a vote loop plus
-// register->uniform moves: 125-220 cycles per instruction against the 64 / 128 cycles the tensor pipe needs.)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-
-constexpr uint32_t TOPK_VAL_MASK = 0xffffffe0u;   // top-k keys: cosine bits with the low 5 mantissa bits replaced by the column's index in its chunk
-
-__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
-
-// Hard-negative top-k (ffc.py:86-92) over 16 raw cosines v[BASE .. BASE+16) of one row (= lane), columns col0 .. col0+15.
-// Branch-free register list of integer keys: only POSITIVE cosines can contribute (clip(.., 0) zeroes the rest and their
-// gradient), positive floats order like their int32 bit patterns, and the low 4 mantissa bits carry the column's index inside
-// the chunk (5 bits: up to 32 columns; value error 2^-18).  tk[] descending keys (0 = empty), tc[] first column of the chunk a key came from.
-// Warp-collective: all lanes run the same code; a lane with a candidate (key above its threshold `kth`) extracts its largest
-// remaining key per round until no lane has any left.  `kfloor` is the row's threshold shared by the column chunks (below).
-// sorted insertion of one key into the branch-free register list (the caller has checked xk > kth)
-__device__ __forceinline__ void topk_insert_key(int xk, int xc, int k, int (&tk)[KMAX], int (&tc)[KMAX]) {
-#pragma unroll
-  for (int r = 0; r < KMAX; ++r) {
-    if (r < k) {
-      const bool pgt = xk > tk[r];
-      const int nk = pgt ? xk : tk[r], nc = pgt ? xc : tc[r];
-      xk = pgt ? tk[r] : xk;
-      xc = pgt ? tc[r] : xc;
-      tk[r] = nk;
-      tc[r] = nc;
-    }
-  }
-}
-
-template <int BASE, int NV>
-__device__ __forceinline__ void topk_scan16(const uint32_t (&v)[NV], uint32_t excl, int col0, bool outl, int k, int (&tk)[KMAX], int (&tc)[KMAX],
-                                            int& kth, int kfloor) {
-  int key[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    key[c] = (int)((v[BASE + c] & TOPK_VAL_MASK) | (uint32_t)c);
-    if ((excl >> c) & 1u) key[c] = 0;
-  }
-  int bound = 0x7fffffff;      // keys >= bound were already extracted in this chunk
-  while (true) {
-    int mx = 0;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) mx = max(mx, key[c] < bound ? key[c] : 0);
-    const bool has = outl && mx > kth;
-    if (!__any_sync(0xffffffffu, has)) break;
-    if (has) {
-      int xk = mx, xc = col0;
-#pragma unroll
-      for (int r = 0; r < KMAX; ++r) {
-        if (r < k) {
-          const bool pgt = xk > tk[r];
-          const int nk = pgt ? xk : tk[r], nc = pgt ? xc : tc[r];
-          xk = pgt ? tk[r] : xk;
-          xc = pgt ? tc[r] : xc;
-          tk[r] = nk;
-          tc[r] = nc;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < KMAX; ++r)
-        if (r == k - 1) kth = max(tk[r], kfloor);     // own k-th, or the row's shared threshold if that is higher
-      bound = mx;
-    } else {
-      bound = 0;               // this lane is done with the chunk
-    }
-  }
-}
 
 #ifndef FFC_SM100_DEBUG_BUILD
 #define FFC_SM100_DEBUG_BUILD 0     // 1: honour Sm100Params::debug (bottleneck isolation, see tools/sweep_modes.py)
@@ -351,36 +122,6 @@ __device__ long long g_sweep_prof[1024][8];
 #define FFC_STAMP(slot) do {} while (0)
 #define FFC_STAMP_NS(slot) do {} while (0)
 #endif
-
-// One launch runs up to MAX_SUB sweeps that share the probe rows P (their work items are concatenated): the main sweep over
-// queue[0] and the two tiny side sweeps over the gathered `ones` rows.  The main sweep of C3 fills 72 of the 74 CTA-pair
-// slots, so the side items run on the two spare pairs while it is in flight instead of as two more launches.
-constexpr int MAX_SUB = 3;
-struct SubSweep {
-  int64_t n_cols;
-  const int32_t* n_cols_dev;
-  const int32_t* tcol;
-  const uint32_t* cmask;
-  const float* thr;
-  int tiles_per_chunk;
-  int item0;          // first work item of this sweep (items are [row tile fastest][column chunk])
-  float* l_part;
-  float* o_part;
-  float* topv_part;
-  int32_t* topi_part;
-};
-struct Sm100Params {
-  int n_rows;
-  const __nv_bfloat16* p16;   // [n_rows, D] probe rows (bf16), loaded straight into TMEM when P_TMEM
-  const uint8_t* is_out;
-  int32_t* kth_shared;        // [n_rows] shared hard-negative threshold (integer key), zeroed by the prep kernel
-  float a2, b2;       // p~ = 2^(a2 * z - b2)
-  int k;
-  int debug;   // bottleneck isolation BITMASK, only in FFC_SM100_DEBUG_BUILD builds; results are WRONG when any bit is set:
-               // 1 = O-CTA skips TMA+MMA, 2 = epilogue skips tcgen05.ld/exp, 4 = S-CTA skips TMA+MMA,
-               // 16 = no P~ hand-off (both CTAs free-run), 64 = no W TMA loads (MMAs run on whatever is in shared memory)
-  SubSweep sub[MAX_SUB];
-};
 
 template <int D>
 struct SweepShape {
@@ -1054,7 +795,7 @@ struct Sm100Cache {
 Sm100Cache* sm100_cache_create() { return new Sm100Cache(); }
 void sm100_cache_destroy(Sm100Cache* c) { delete c; }
 
-static int get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_rows, bool chunked3d, CUtensorMap* out) {
+int sm100_get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_rows, bool chunked3d, CUtensorMap* out) {
   MapKey key{ptr, rows, D, chunked3d ? -box_rows : box_rows};
   for (auto& e : c->maps)
     if (e.first == key) {
@@ -1098,21 +839,29 @@ static int get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_
   return FFC_OK;
 }
 
+// D <= 256 runs on the one-CTA kernel (head_sm100_1cta.cu) unless FFC_SWEEP_PAIR=1 asks for the CTA-pair kernel (A/B measurements)
+static bool use_one_cta(int D) {
+  static const bool force_pair = getenv("FFC_SWEEP_PAIR") != nullptr && atoi(getenv("FFC_SWEEP_PAIR")) != 0;
+  return D <= 256 && !force_pair;
+}
+
 int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
-  (void)D;
-  // items = row_tiles x chunks run as CTA pairs, 74 pairs at a time: pick the chunk count whose last wave is fullest
-  // (ties -> fewer chunks: fewer partials and fewer P loads / O write-outs)
+  // items = row_tiles x chunks run as CTA pairs, 74 pairs at a time (one-CTA kernel: 148 CTAs): pick the chunk count whose last
+  // wave is fullest (ties -> fewer chunks: fewer partials and fewer P loads / O write-outs)
+  const bool one = use_one_cta(D);
+  const int slots = one ? 148 : 74;
+  const int tile_cols = one ? sm100_1cta_tile_cols(D) : BN;
   const int row_tiles = std::max(1, (n_rows + BM - 1) / BM);
-  const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(n_cols, BN));
+  const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(n_cols, tile_cols));
   const int max_c = (int)std::min<int64_t>(n_tiles, 40);
   int best = 1;
   double best_eff = 0.0;
   for (int c = 1; c <= max_c; ++c) {
     const int items = row_tiles * c;
-    const int waves = (items + 73) / 74;
-    // every item pays a fixed cost (prologue, P load, O write-out) worth about 12 tile-times
-    const double tiles_per_item = (double)n_tiles / c;
-    const double eff = ((double)items / (waves * 74.0)) * (tiles_per_item / (tiles_per_item + 12.0));
+    const int waves = (items + slots - 1) / slots;
+    // every item pays a fixed cost (prologue, P load, O write-out) worth about 12 tile-times (of 128 columns)
+    const double tiles_per_item = (double)n_tiles / c * tile_cols / 128.0;
+    const double eff = ((double)items / (waves * (double)slots)) * (tiles_per_item / (tiles_per_item + 12.0));
     if (eff > best_eff * 1.005) {
       best_eff = eff;
       best = c;
@@ -1173,12 +922,13 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
 // weight matrix, exclusions, chunk count and partial outputs.
 int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps, cudaStream_t s) {
   FFC_REQUIRE(n_sweeps >= 1 && n_sweeps <= MAX_SUB, "tcgen05 sweep: %d sweeps per launch (1..%d)", n_sweeps, MAX_SUB);
+  if (use_one_cta(sweeps[0].D)) return launch_sweeps_sm100_1cta(cache, sweeps, n_sweeps, s);
   const SweepArgs& a = sweeps[0];
   FFC_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256 || a.D == 512, "tcgen05 sweep: D=%d must be 64, 128, 256 or 512", a.D);
   FFC_REQUIRE(a.P_bf16, "tcgen05 sweep: bf16 operands missing");
   CUtensorMap maps[1 + 2 * MAX_SUB];
   int rc;
-  if ((rc = get_map(cache, a.P_bf16, a.n_rows, a.D, BM, false, &maps[0]))) return rc;
+  if ((rc = sm100_get_map(cache, a.P_bf16, a.n_rows, a.D, BM, false, &maps[0]))) return rc;
   Sm100Params p;
   memset(&p, 0, sizeof(p));
   p.n_rows = a.n_rows;
@@ -1208,8 +958,8 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
     const SweepArgs& w = sweeps[i];
     FFC_REQUIRE(w.W_bf16 && w.n_rows == a.n_rows && w.D == a.D && w.P_bf16 == a.P_bf16 && w.sv == a.sv && w.k == a.k && w.n_chunks >= 1,
                 "tcgen05 sweep: sweep %d does not share the probe rows / shape of sweep 0", i);
-    if ((rc = get_map(cache, w.W_bf16, w.n_cols, w.D, BN, false, &maps[1 + 2 * i]))) return rc;
-    if ((rc = get_map(cache, w.W_bf16, w.n_cols, w.D, JB, true, &maps[2 + 2 * i]))) return rc;
+    if ((rc = sm100_get_map(cache, w.W_bf16, w.n_cols, w.D, BN, false, &maps[1 + 2 * i]))) return rc;
+    if ((rc = sm100_get_map(cache, w.W_bf16, w.n_cols, w.D, JB, true, &maps[2 + 2 * i]))) return rc;
     sb.n_cols = w.n_cols;
     sb.n_cols_dev = w.n_cols_dev;
     sb.tcol = w.tcol;

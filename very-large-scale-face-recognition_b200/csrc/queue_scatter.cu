@@ -9,10 +9,18 @@
 
 namespace ffc {
 
-__device__ __forceinline__ bool later_duplicate(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int i, int B) {
+// Is there a later position with the same (row, col)?  `packed`: the live positions come first and every position after the first
+// padded one (cols < 0) is padded too -- the sharded head's lists, where a rank's own keys are compacted to the front of the R*B
+// gathered positions -- so the scan stops there (at 8 ranks 7/8 of the list is padding: 80 us -> 10 us per scatter).
+__device__ __forceinline__ bool later_duplicate(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int i, int B, bool packed) {
   const int32_t r = rows[i], c = cols[i];
   bool dup = false;
-  for (int j = i + 1 + threadIdx.x; j < B; j += blockDim.x) dup |= (cols[j] == c && rows[j] == r);
+  for (int j0 = i + 1; j0 < B; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    const int32_t cj = j < B ? cols[j] : -1;
+    dup |= (cj == c && rows[j < B ? j : i] == r);
+    if (packed && __syncthreads_or(cj < 0)) break;
+  }
   return __syncthreads_or(dup);
 }
 
@@ -30,7 +38,7 @@ __global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ 
                                                             int32_t* __restrict__ ovl_map, int ovl_table) {
   const int i = blockIdx.x;
   if (cols[i] < 0) return;   // padded position (sharded callers)
-  if (later_duplicate(rows, cols, i, B)) return;
+  if (later_duplicate(rows, cols, i, B, src_row != nullptr)) return;
   const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
   if (ovl_map && threadIdx.x == 0) {
     // overlay of the sharded head's merged step (csrc/head.cu FinalizeArgs::ovl_map): where the sweep-time content of this (row, slot)
@@ -52,10 +60,10 @@ __global__ void __launch_bounds__(128) queue_scatter_kernel(float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(128) queue_restore_kernel(float* __restrict__ qf, __nv_bfloat16* __restrict__ qh, const int32_t* __restrict__ rows,
-                                                            const int32_t* __restrict__ cols, const float* __restrict__ undo, int B, int64_t Q, int D) {
+                                                            const int32_t* __restrict__ cols, const float* __restrict__ undo, int B, int64_t Q, int D, int packed) {
   const int i = blockIdx.x;
   if (cols[i] < 0) return;
-  if (later_duplicate(rows, cols, i, B)) return;
+  if (later_duplicate(rows, cols, i, B, packed != 0)) return;
   const int64_t off = ((int64_t)rows[i] * Q + cols[i]) * D;
   const float4* src = reinterpret_cast<const float4*>(undo + (int64_t)i * D);
   float4* dst = reinterpret_cast<float4*>(qf + off);
@@ -299,7 +307,7 @@ extern "C" int ffc_queue_restore(float* queue_f32_dev, void* queue_bf16_dev, con
   if (rc) return rc;
   FFC_REQUIRE(undo_f32_dev != nullptr, "ffc_queue_restore: undo buffer is NULL");
   if (B == 0) return FFC_OK;
-  queue_restore_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, undo_f32_dev, B, Q, D);
+  queue_restore_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, undo_f32_dev, B, Q, D, 0);
   FFC_LAUNCH_CHECK();
   return FFC_OK;
 }
@@ -310,6 +318,17 @@ extern "C" int ffc_cast_bf16(const float* src_dev, void* dst_bf16_dev, int64_t n
   const int64_t n4 = n / 4;
   const int blocks = (int)std::min<int64_t>(ceil_div64(n4, 256), 148 * 16);
   cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src_dev, (uint2*)dst_bf16_dev, n4);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_queue_restore_packed(float* queue_f32_dev, void* queue_bf16_dev, const int32_t* rows_dev, const int32_t* cols_dev,
+                                        const float* undo_f32_dev, int B, int64_t Q, int D, void* stream) {
+  int rc = check_scatter_args(queue_f32_dev, rows_dev, cols_dev, B, Q, D);
+  if (rc) return rc;
+  FFC_REQUIRE(undo_f32_dev != nullptr, "ffc_queue_restore_packed: undo buffer is NULL");
+  if (B == 0) return FFC_OK;
+  queue_restore_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(queue_f32_dev, (__nv_bfloat16*)queue_bf16_dev, rows_dev, cols_dev, undo_f32_dev, B, Q, D, 1);
   FFC_LAUNCH_CHECK();
   return FFC_OK;
 }

@@ -62,6 +62,7 @@ PROTOTYPES = {
     'ffc_lru_import': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'ffc_queue_scatter': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     'ffc_queue_restore': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    'ffc_queue_restore_packed': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     'ffc_cast_bf16': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'ffc_head_create': (c_int, [C.POINTER(HeadConfig), C.POINTER(c_void_p)]),
     'ffc_head_destroy': (c_int, [c_void_p]),

@@ -146,7 +146,7 @@ class CudaShardBackend:
         self.lru.undo(-1, self.qpos)
 
     def restore_queue(self):
-        check(self.lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
+        check(self.lib.ffc_queue_restore_packed(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
                                          self.undo_rows.data_ptr(), self._set['n'], self.Ql, self.D, self._s()))
 
     def view(self, keys):
