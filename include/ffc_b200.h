@@ -328,6 +328,16 @@ int ffc_head_finalize_gathered_ex(ffc_head_t* h, const ffc_head_pass* in, const 
                                   int64_t record_stride_words, const ffc_head_finalize_opts* opts, float* loss_out,
                                   float* dp_out, void* stream);
 
+/* Optional mode, off by default: dLoss/dQueue.  The reference keeps `queue` a no-grad buffer (ffc.py:29); a caller that trains the
+ * prototypes enables the mode before a pass (ffc_head_set_dqueue: the fused finalize then also exports its per-row coefficients)
+ * and, after ffc_head_pass_single / ffc_head_finalize_gathered[_ex] of that pass and before the queue rows change again, calls
+ * ffc_head_dqueue: dqueue_out [2, q_local, D] fp32 is OVERWRITTEN with d(loss of the pass)/d(queue) for an upstream gradient of 1 --
+ * both add_margin terms (ffc.py:195-202 through autograd, had `queue` required grad) incl. the hard-negative rows.  One more sweep
+ * of the tcgen05 kernel with the roles of queue and probe rows swapped (4 n Q D FLOPs, no B x Q matrix) plus two small kernels for
+ * the target / `ones` rows and the hard negatives.  bf16 AM / Arc only.  `in` = the pass just finalized. */
+int ffc_head_set_dqueue(ffc_head_t* h, int enable);
+int ffc_head_dqueue(ffc_head_t* h, const ffc_head_pass* in, float* dqueue_out, void* stream);
+
 /* sizes in bytes of the five stats arrays for n rows (one rank's worth) */
 int ffc_head_stats_bytes(const ffc_head_config* cfg, int n_rows, int64_t sizes_out[5]);
 

@@ -155,3 +155,22 @@ class HeadOracle:
         loss2 = self.head_pass(x, y, x_label, y_label, commit=False)
         loss1 = self.head_pass(y, x, y_label, x_label, commit=True)
         return loss1 + loss2
+
+
+def dqueue_ref(p, queue, label, ones, loss_type, margin, scale, k):
+    """dLoss/dQueue of ONE head pass by autograd, had the reference's `queue` required grad (it is a no-grad buffer, ffc.py:29; the
+    optional mode of north_star): `queue` [2,Q,D] is the queue as the pass sweeps it (after its enqueue), `label` the probe labels
+    (ffc.py:189-194), `ones` the slots whose second row the blended weight reads (ffc.py:197-200).  Returns (loss, dqueue [2,Q,D])."""
+    w = queue.detach().clone().requires_grad_(True)
+    w0 = w[0]
+    if len(ones):
+        m = torch.zeros(w.shape[1], 1, dtype=w.dtype)
+        m[torch.as_tensor(ones, dtype=torch.long)] = 1.0
+        w2 = m * w[1] + (1.0 - m) * w[0]                  # ffc.py:200
+    else:
+        w2 = w0
+    p = p.detach().to(w.dtype)
+    lab = torch.as_tensor(label, dtype=torch.long)
+    loss = add_margin(p @ w0.t(), lab, loss_type, margin, scale, k) + add_margin(p @ w2.t(), lab, loss_type, margin, scale, k)
+    (g,) = torch.autograd.grad(loss, w)
+    return loss.detach(), g

@@ -47,6 +47,14 @@ struct ffc_head {
   float* topv_part;
   int32_t* topi_part;
   ffc::Sm100Cache* sm100;
+  // queue-gradient mode (ffc_head_set_dqueue / ffc_head_dqueue)
+  int want_dq;
+  __nv_bfloat16* pc16;         // [max_rows][D] probe rows scaled by their softmax coefficients (GEMM-2 operand of the swapped sweep)
+  float* dq_l;                 // [q_local] scratch partials of the swapped sweep (denominators: unused)
+  float* dq_tv;                // [q_local]
+  int32_t* dq_ti;              // [q_local]
+  int32_t* dq_claim;           // [q_local] which call last claimed a special slot
+  int32_t dq_epoch;
   // optional device timing of the main sweep kernel (bench / roofline evidence)
   int timing;
   std::vector<cudaEvent_t>* ev;   // pairs (start, stop), recorded on the launch stream
@@ -551,6 +559,12 @@ struct FinalizeArgs {
   const int32_t* ovl_map;
   const float* ovl_g;
   const float* ovl_undo;
+  // Optional export of the per-row scalars (queue-gradient mode, ffc_head_dqueue): coef [4][n] (cO loss 1 / 2, cT loss 1 / 2), the
+  // hard-negative slot lists of outlier rows
+  float* coef_out;
+  int32_t* nslot_out;
+  int32_t* wslot_out;
+  uint8_t* wrow_out;
   // Output routing (reduce-scatter folded into finalize): with dp_peer != NULL row i of this rank's partial dLoss/dp is stored to
   // dp_peer[i / dp_rows_per_rank] + dp_slot_off + (i % dp_rows_per_rank) * D -- the owner rank's peer-mapped staging buffer
   // (stores travel over NVLink) -- instead of dp[i * D].
@@ -878,6 +892,17 @@ __global__ void __launch_bounds__(128) head_finalize_fused_kernel(const ReduceJo
     s_coef[r][2] = cT[0];
     s_coef[r][3] = cT[1];
     s_nw[r] = nw;
+    if (a.coef_out) {
+      a.coef_out[0 * n + i] = cO[0];
+      a.coef_out[1 * n + i] = cO[1];
+      a.coef_out[2 * n + i] = cT[0];
+      a.coef_out[3 * n + i] = cT[1];
+      a.nslot_out[i] = nw;
+      for (int x = 0; x < nw; ++x) {
+        a.wslot_out[(int64_t)i * 2 * KMAX + x] = s_wslot[r][x];
+        a.wrow_out[(int64_t)i * 2 * KMAX + x] = s_wrow[r][x];
+      }
+    }
   }
   if (tid < FR && row0 + tid < n) {      // the rows' prototype rows (through the overlay), resolved once per row
     const int i = row0 + tid;
@@ -1106,6 +1131,11 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
   cudaFree(h->tpos);
   cudaFree(h->is_out);
   cudaFree(h->kth_shared);
+  cudaFree(h->pc16);
+  cudaFree(h->dq_l);
+  cudaFree(h->dq_tv);
+  cudaFree(h->dq_ti);
+  cudaFree(h->dq_claim);
   cudaFree(h->thr);
   cudaFree(h->counts);
   cudaFree(h->row_loss);
@@ -1392,6 +1422,12 @@ static FinalizeArgs make_finalize_args(ffc_head_t* h, const ffc_head_pass* in, c
   a.sin_m = sin((double)c.margin);
   a.row_loss = h->row_loss;
   a.dp = dp_out;
+  if (h->want_dq) {
+    a.coef_out = h->coef;
+    a.nslot_out = h->nslot;
+    a.wslot_out = h->wslot;
+    a.wrow_out = h->wrow;
+  }
   return a;
 }
 
@@ -1493,5 +1529,171 @@ extern "C" int ffc_head_get_timing(ffc_head_t* h, double* total_ms_out, int64_t*
   }
   *total_ms_out = tot;
   *launches_out = (int64_t)(h->ev_used / 2);
+  return FFC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optional mode: dLoss/dQueue (the reference keeps `queue` a no-grad buffer, ffc.py:29; north_star asks for "dQueue where the queue
+// is trainable").  For the pass just finalized, with z_ij = s cos_ij (j != t_i), L_l,i the softmax denominators and
+// a_l,i = s / (n_pos L_l,i) (finalize's cO), every queue row gets
+//     dqueue[0][j] = sum_i (a_1i + a_2i) p~_ij p_i                                  for j outside C u T   (the bulk: Q x n x D)
+// -- the SAME sweep kernel with the roles swapped: the queue rows are the "probe rows", the n probe embeddings the columns, GEMM-1
+// recomputes the cosines from the bf16 probe rows and GEMM-2 accumulates the probe rows scaled by their coefficient (W2 operand),
+// so dqueue[0] comes out of TMEM row tile by row tile: 4 n Q D more FLOPs per pass, no B x Q matrix.  The <= 2n "special" slots --
+// targets T (the margin changes their coefficient) and `ones` C (losses 1 / 2 read different rows) -- are recomputed exactly by a
+// small SIMT kernel and overwritten; the hard-negative term adds w_neg p_i to the <= 2k rows each outlier row selected.
+// ------------------------------------------------------------------------------------------------
+namespace ffc {
+
+__global__ void __launch_bounds__(128) dq_scale_probe_kernel(const __nv_bfloat16* __restrict__ p16, const float* __restrict__ coef, const uint8_t* __restrict__ is_out,
+                                                             int n, int D, __nv_bfloat16* __restrict__ pc16) {
+  const int i = blockIdx.x;
+  const float c = is_out[i] ? 0.f : coef[0 * n + i] + coef[1 * n + i];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) pc16[(int64_t)i * D + d] = __float2bfloat16(c * __bfloat162float(p16[(int64_t)i * D + d]));
+}
+
+// one block per candidate special slot: blocks [0, max_rows) take ones_list[b] (if b < n_ones), blocks [max_rows, max_rows + n) the
+// target of probe row b - max_rows (if it is local, not in C -- those are the first kind -- and not claimed by another row's block)
+__global__ void __launch_bounds__(256) dq_special_rows_kernel(const __nv_bfloat16* __restrict__ p16, const __nv_bfloat16* __restrict__ qh, int64_t q_local, int D, int n,
+                                                              int max_rows, const int32_t* __restrict__ ones_list, const int32_t* __restrict__ n_ones_p,
+                                                              const uint32_t* __restrict__ cmask_unused, const int32_t* __restrict__ tcol,
+                                                              const int32_t* __restrict__ tpos, const uint8_t* __restrict__ is_out, const float* __restrict__ coef,
+                                                              float a2, float b2, int32_t* __restrict__ claim, int32_t epoch, float* __restrict__ dq) {
+  extern __shared__ float sm[];          // [D] queue row, [n] coefficients
+  float* s_q = sm;
+  float* s_c = sm + D;
+  const int b = blockIdx.x;
+  int slot;
+  bool in_c;
+  if (b < max_rows) {
+    if (b >= *n_ones_p) return;
+    slot = ones_list[b];
+    in_c = true;
+  } else {
+    const int i = b - max_rows;
+    if (i >= n || is_out[i] || tcol[i] < 0 || tpos[i] >= 0) return;      // tpos >= 0: the target is in C
+    slot = tcol[i];
+    in_c = false;
+    __shared__ int mine;
+    if (threadIdx.x == 0) mine = atomicExch(&claim[slot], epoch) != epoch;
+    __syncthreads();
+    if (!mine) return;
+  }
+  for (int r = 0; r < (in_c ? 2 : 1); ++r) {
+    const __nv_bfloat16* qrow = qh + ((int64_t)r * q_local + slot) * D;
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) s_q[d] = __bfloat162float(qrow[d]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float c = 0.f;
+      if (!is_out[i]) {
+        const bool is_t = tcol[i] == slot;
+        if (is_t) {
+          // the target column: d/dcos of the margined logit, from finalize (cT); loss 2 reads queue[1] iff the slot is in C
+          if (r == 0) c += coef[2 * n + i];
+          if (r == (in_c ? 1 : 0)) c += coef[3 * n + i];
+        } else {
+          const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(p16 + (int64_t)i * D);
+          float dot = 0.f;
+          for (int d = 0; d < D; d += 2) {
+            const float2 v = __bfloat1622float2(pr[d >> 1]);
+            dot = fmaf(v.x, s_q[d], dot);
+            dot = fmaf(v.y, s_q[d + 1], dot);
+          }
+          const float pt = exp2f(fmaf(dot, a2, -b2));
+          c = in_c ? coef[r * n + i] * pt : (coef[0 * n + i] + coef[1 * n + i]) * pt;
+        }
+      }
+      s_c[i] = c;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) acc = fmaf(s_c[i], __bfloat162float(p16[(int64_t)i * D + d]), acc);
+      dq[((int64_t)r * q_local + slot) * D + d] = acc;
+    }
+  }
+}
+
+// hard negatives (ffc.py:86-92): outlier row i adds w_neg p_i to the prototype rows finalize selected for it
+__global__ void __launch_bounds__(128) dq_hard_neg_kernel(const __nv_bfloat16* __restrict__ p16, const uint8_t* __restrict__ is_out, const float* __restrict__ coef,
+                                                          const int32_t* __restrict__ nslot, const int32_t* __restrict__ wslot, const uint8_t* __restrict__ wrow, int n,
+                                                          int D, int64_t q_local, int64_t col_offset, float* __restrict__ dq) {
+  const int i = blockIdx.x;
+  if (!is_out[i]) return;
+  const float w = coef[0 * n + i];
+  const int nw = nslot[i];
+  for (int x = 0; x < nw; ++x) {
+    const int64_t loc = (int64_t)wslot[(int64_t)i * 2 * KMAX + x] - col_offset;
+    if (loc < 0 || loc >= q_local) continue;
+    float* dst = dq + ((int64_t)wrow[(int64_t)i * 2 * KMAX + x] * q_local + loc) * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(dst + d, w * __bfloat162float(p16[(int64_t)i * D + d]));
+  }
+}
+
+}  // namespace ffc
+
+extern "C" int ffc_head_set_dqueue(ffc_head_t* h, int enable) {
+  FFC_REQUIRE(h != nullptr, "ffc_head_set_dqueue: NULL handle");
+  FFC_REQUIRE(!enable || (h->cfg.precision == FFC_PREC_BF16 && h->cfg.loss_type != FFC_LOSS_SV), "ffc_head_set_dqueue: the queue-gradient mode is built for the bf16 AM / Arc head");
+  if (enable && !h->pc16) {
+    const int64_t R = h->cfg.max_rows, D = h->cfg.feat_dim, Q = h->cfg.q_local;
+    FFC_CUDA(cudaMalloc(&h->pc16, R * D * sizeof(__nv_bfloat16)));
+    FFC_CUDA(cudaMalloc(&h->dq_l, Q * sizeof(float)));
+    FFC_CUDA(cudaMalloc(&h->dq_tv, Q * sizeof(float)));
+    FFC_CUDA(cudaMalloc(&h->dq_ti, Q * sizeof(int32_t)));
+    FFC_CUDA(cudaMalloc(&h->dq_claim, Q * sizeof(int32_t)));
+    FFC_CUDA(cudaMemset(h->dq_claim, 0, Q * sizeof(int32_t)));
+  }
+  h->want_dq = enable ? 1 : 0;
+  return FFC_OK;
+}
+
+extern "C" int ffc_head_dqueue(ffc_head_t* h, const ffc_head_pass* in, float* dqueue_out, void* stream) {
+  FFC_REQUIRE(h && in && dqueue_out, "ffc_head_dqueue: NULL argument");
+  FFC_REQUIRE(h->want_dq, "ffc_head_dqueue: enable the mode with ffc_head_set_dqueue before the pass");
+  const ffc_head_config& c = h->cfg;
+  const int n = in->n_rows, D = c.feat_dim;
+  FFC_REQUIRE(n >= 1 && n <= c.max_rows && in->queue_bf16 && in->ones_list && in->n_ones, "ffc_head_dqueue: bad pass description");
+  FFC_REQUIRE(c.q_local < ((int64_t)1 << 31) / 2, "ffc_head_dqueue: shard too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  const __nv_bfloat16* qh = (const __nv_bfloat16*)in->queue_bf16;
+  dq_scale_probe_kernel<<<n, 128, 0, s>>>(h->p16, h->coef, h->is_out, n, D, h->pc16);
+  FFC_LAUNCH_CHECK();
+  // the swapped sweep: "probe rows" = the queue rows of queue[0], columns = the n probe embeddings
+  SweepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P_bf16 = qh;
+  a.n_rows = (int)c.q_local;
+  a.D = D;
+  a.W_bf16 = h->p16;
+  a.W2_bf16 = h->pc16;
+  a.force_pair = 1;
+  a.n_cols = n;
+  a.kth_shared = h->kth_shared;
+  a.scale = c.scale;
+  a.fixed_max = fixed_max_of(c);
+  a.k = 1;
+  a.n_chunks = 1;
+  a.l_part = h->dq_l;
+  a.o_part = dqueue_out;
+  a.topv_part = h->dq_tv;
+  a.topi_part = h->dq_ti;
+  int rc = launch_sweeps_sm100(h->sm100, &a, 1, s);
+  if (rc) return rc;
+  FFC_CUDA(cudaMemsetAsync(dqueue_out + c.q_local * D, 0, (size_t)c.q_local * D * sizeof(float), s));
+  h->dq_epoch += 1;
+  const size_t smem = (size_t)(D + n) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FFC_CUDA(cudaFuncSetAttribute(dq_special_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  FFC_REQUIRE(smem <= 200 * 1024, "ffc_head_dqueue: %d rows exceed the special-row kernel's shared memory", n);
+  dq_special_rows_kernel<<<c.max_rows + n, 256, smem, s>>>(h->p16, qh, c.q_local, D, n, c.max_rows, in->ones_list, in->n_ones, in->cmask, h->tcol, h->tpos, h->is_out, h->coef,
+                                                           c.scale * 1.4426950408889634f, fixed_max_of(c) * 1.4426950408889634f, h->dq_claim, h->dq_epoch, dqueue_out);
+  FFC_LAUNCH_CHECK();
+  dq_hard_neg_kernel<<<n, 128, 0, s>>>(h->p16, h->is_out, h->coef, h->nslot, h->wslot, h->wrow, n, D, c.q_local, c.col_offset, dqueue_out);
+  FFC_LAUNCH_CHECK();
   return FFC_OK;
 }

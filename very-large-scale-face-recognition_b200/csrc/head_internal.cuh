@@ -15,6 +15,9 @@ constexpr float SV_T = 1.2f;  // ffc.py:47 mask_svfc
 struct SweepArgs {
   const float* W_f32;            // [n_cols, D] (check mode)
   const __nv_bfloat16* W_bf16;   // [n_cols, D] (tensor-core mode)
+  const __nv_bfloat16* W2_bf16;  // optional: the matrix GEMM-2 accumulates (O += p~ . W2) when it is not W itself -- the queue-gradient
+                                 // sweep reads the probe rows for the cosines and the coefficient-scaled probe rows for the sum.  CTA-pair kernel only.
+  int force_pair;                // run on the CTA-pair kernel whatever D is
   const float* P_f32;            // [n_rows, D]
   const __nv_bfloat16* P_bf16;   // [n_rows, D]
   int64_t n_cols;                // host-side bound on the number of columns

@@ -321,8 +321,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       const int r_local = q4 * 32 + lane;         // row within the item
       const int row = row0 + r_local;
       const bool row_ok = row < prm.n_rows;
-      const int32_t tcol = row_ok ? sw.tcol[row] : -1;
-      const bool outl = row_ok && prm.is_out[row];
+      const int32_t tcol = (row_ok && sw.tcol) ? sw.tcol[row] : -1;
+      const bool outl = row_ok && prm.is_out && prm.is_out[row];
       const bool warp_out = __any_sync(0xffffffffu, outl);
       float thr = INFINITY;
       if (SV && row_ok && sw.thr) thr = sw.thr[row];
@@ -922,7 +922,7 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
 // weight matrix, exclusions, chunk count and partial outputs.
 int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps, cudaStream_t s) {
   FFC_REQUIRE(n_sweeps >= 1 && n_sweeps <= MAX_SUB, "tcgen05 sweep: %d sweeps per launch (1..%d)", n_sweeps, MAX_SUB);
-  if (use_one_cta(sweeps[0].D)) return launch_sweeps_sm100_1cta(cache, sweeps, n_sweeps, s);
+  if (use_one_cta(sweeps[0].D) && !sweeps[0].force_pair) return launch_sweeps_sm100_1cta(cache, sweeps, n_sweeps, s);
   const SweepArgs& a = sweeps[0];
   FFC_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256 || a.D == 512, "tcgen05 sweep: D=%d must be 64, 128, 256 or 512", a.D);
   FFC_REQUIRE(a.P_bf16, "tcgen05 sweep: bf16 operands missing");
@@ -959,7 +959,7 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
     FFC_REQUIRE(w.W_bf16 && w.n_rows == a.n_rows && w.D == a.D && w.P_bf16 == a.P_bf16 && w.sv == a.sv && w.k == a.k && w.n_chunks >= 1,
                 "tcgen05 sweep: sweep %d does not share the probe rows / shape of sweep 0", i);
     if ((rc = sm100_get_map(cache, w.W_bf16, w.n_cols, w.D, BN, false, &maps[1 + 2 * i]))) return rc;
-    if ((rc = sm100_get_map(cache, w.W_bf16, w.n_cols, w.D, JB, true, &maps[2 + 2 * i]))) return rc;
+    if ((rc = sm100_get_map(cache, w.W2_bf16 ? w.W2_bf16 : w.W_bf16, w.n_cols, w.D, JB, true, &maps[2 + 2 * i]))) return rc;
     sb.n_cols = w.n_cols;
     sb.n_cols_dev = w.n_cols_dev;
     sb.tcol = w.tcol;

@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int r_local = q4 * 32 + lane;
     const int row = row0 + r_local;
     const bool row_ok = row < prm.n_rows;
-    const int32_t tcol = row_ok ? sw.tcol[row] : -1;
-    const bool outl = row_ok && prm.is_out[row];
+    const int32_t tcol = (row_ok && sw.tcol) ? sw.tcol[row] : -1;
+    const bool outl = row_ok && prm.is_out && prm.is_out[row];
     const bool warp_out = __any_sync(0xffffffffu, outl);
     float thr = INFINITY;
     if (SV && row_ok && sw.thr) thr = sw.thr[row];
@@ -459,6 +459,7 @@ int launch_sweeps_sm100_1cta(Sm100Cache* cache, const SweepArgs* sweeps, int n_s
   const SweepArgs& a = sweeps[0];
   FFC_REQUIRE(a.D == 64 || a.D == 128 || a.D == 256, "one-CTA tcgen05 sweep: D=%d must be 64, 128 or 256", a.D);
   FFC_REQUIRE(a.P_bf16, "tcgen05 sweep: bf16 operands missing");
+  FFC_REQUIRE(!a.W2_bf16, "one-CTA tcgen05 sweep: both GEMMs read the same tile (W2 needs the CTA-pair kernel)");
   const int BN = sm100_1cta_tile_cols(a.D);
   CUtensorMap maps[MAX_SUB];
   Sm100Params p;

@@ -86,6 +86,8 @@ PROTOTYPES = {
     'ffc_tail_workspace_bytes': (c_int, [c_int, c_int, C.POINTER(c_int64)]),
     'ffc_tail_forward': (c_int, [C.POINTER(TailArgs), c_void_p]),
     'ffc_tail_backward': (c_int, [C.POINTER(TailArgs), c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ffc_head_set_dqueue': (c_int, [c_void_p, c_int]),
+    'ffc_head_dqueue': (c_int, [c_void_p, C.POINTER(HeadPass), c_void_p, c_void_p]),
     'ffc_head_set_timing': (c_int, [c_void_p, c_int]),
     'ffc_head_get_timing': (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64)]),
     'ffc_head_stats_bytes': (c_int, [C.POINTER(HeadConfig), c_int, C.POINTER(c_int64)]),

@@ -90,7 +90,7 @@ class _HeadPairFn(torch.autograd.Function):
 class FFCHead(Module):
     """State and kernels of the FFC head: prototype queue [2,Q,D] (+ bf16 mirror), device LRU, queue positions."""
 
-    def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024, device=None):
+    def __init__(self, feat_dim, queue_size, scale=32.0, loss_type='AM', margin=0.4, precision='bf16', max_batch=1024, device=None, queue_grad=False):
         super().__init__()
         assert loss_type in ('AM', 'Arc', 'SV')
         assert precision in _capi.PRECISIONS
@@ -99,6 +99,12 @@ class FFCHead(Module):
         self.precision = precision
         self.hard_neg = hard_neg_k(self.queue_size)
         self.max_batch = int(max_batch)
+        # Optional, off by default (the reference's queue is a no-grad buffer, ffc.py:29): also compute dLoss/dQueue.  After every head
+        # pass `dqueue_pass` [2, Q, D] holds d(loss of that pass)/d(queue as the pass swept it) for an upstream gradient of 1, and
+        # `dqueue` accumulates it over passes until zero_dqueue() -- a caller that trains the prototypes applies it after
+        # loss.backward(), multiplied by whatever factor scales the loss (a GradScaler's).  bf16 AM / Arc.
+        self.queue_grad = bool(queue_grad)
+        self.dqueue = self.dqueue_pass = None
         q = torch.rand(2, self.queue_size, self.feat_dim, device=device)                                     # ffc.py:29-30
         q /= q.norm(dim=2, keepdim=True).clamp_min(1e-12)
         self.register_buffer('queue', q)
@@ -147,6 +153,10 @@ class FFCHead(Module):
             h = C.c_void_p()
             check(self._lib.ffc_head_create(C.byref(cfg), C.byref(h)))
             self._h, self._cfg = h, cfg
+            if self.queue_grad:
+                check(self._lib.ffc_head_set_dqueue(h, 1))
+                self.dqueue = torch.zeros(2, Q, D, dtype=torch.float32, device=dev)
+                self.dqueue_pass = torch.empty(2, Q, D, dtype=torch.float32, device=dev)
         self._dev = dev
         self.sync_mirror()
         if self._pending_lru is not None:
@@ -190,6 +200,11 @@ class FFCHead(Module):
         self._side.synchronize()          # bookkeeping enqueued by earlier passes
         self._lru_sync_main = True        # whatever the caller does with it happens on the caller's stream
         return self._lru
+
+    def zero_dqueue(self):
+        """Reset the accumulated queue gradient (queue_grad=True)."""
+        if self.dqueue is not None:
+            self.dqueue.zero_()
 
     def set_timing(self, enable):
         """Bracket every main-sweep launch with CUDA events (roofline evidence for bench.py)."""
@@ -277,6 +292,9 @@ class FFCHead(Module):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         # ffc.py:195-202 / 248-254 + backward
         check(lib.ffc_head_pass_single(self._h, C.byref(hp), C.byref(hs), loss.data_ptr(), dp.data_ptr(), s))
+        if self.queue_grad:      # while the queue still is what the pass swept (a rollback pass restores its rows next)
+            check(lib.ffc_head_dqueue(self._h, C.byref(hp), self.dqueue_pass.data_ptr(), s))
+            self.dqueue.add_(self.dqueue_pass)
         if not commit:   # ffc.py:255: the queue rows come back; the LRU was undone by the bookkeeping stream
             check(lib.ffc_queue_restore(self.queue.data_ptr(), self.queue_bf16.data_ptr(), self.rows.data_ptr(), self.cols.data_ptr(),
                                         self.undo_rows.data_ptr(), B, Q, D, s))
