@@ -63,9 +63,24 @@ def test_sweep_kernel_uses_tcgen05_tmem_tma(sass):
     assert any('STTM' in b for b in sweeps.values())            # tcgen05.st: probe tile into TMEM
 
 
+def test_one_cta_sweep_keeps_both_operands_of_gemm2_out_of_shared_memory(sass):
+    """the D <= 256 kernel (csrc/head_sm100_1cta.cu): tcgen05.mma with TMEM A operands for BOTH GEMMs, p~ written back with
+    tcgen05.st (STTM.x16) over the S columns -- no st.async / DSMEM hand-off (STAS) and no cluster barrier traffic"""
+    fns = _functions(sass)
+    ones = {k: v for k, v in fns.items() if 'ffc_head_sweep1_sm100_kernel' in k}
+    assert len(ones) >= 6                                       # {SV, not SV} x D 64 / 128 / 256
+    for name, body in ones.items():
+        for mnemonic in ('UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'SYNCS'):
+            assert mnemonic in body, (name, mnemonic)
+        assert 'STTM.x16' in body or 'STTM.16' in body or re.search(r'STTM\S*x16', body), name
+        assert 'STAS' not in body and not re.search(r'\bHMMA\b', body), name
+        assert len(re.findall(r'UTCHMMA', body)) >= 8, name
+
+
 def test_every_kernel_family_is_in_the_library(sass):
     fns = ' '.join(_functions(sass))
     for family in ('lru_', 'queue_scatter_kernel', 'queue_restore_kernel', 'route_keys', 'head_prep_fused_kernel', 'head_finalize_fused_kernel',
                    'head_sweep_simt_kernel', 'ema_update_kernel', 'tail_rows_fwd_kernel', 'tail_col_stats_kernel', 'tail_rows_bwd_bn_kernel',
-                   'tail_cols_dx_kernel', 'head_thr_from_tgt_kernel'):
+                   'tail_cols_dx_kernel', 'head_thr_from_tgt_kernel', 'sum_slabs_barrier_kernel', 'overlay_clear_kernel', 'dq_special_rows_kernel',
+                   'dq_hard_neg_kernel', 'ffc_head_sweep1_sm100_kernel'):
         assert family in fns, family

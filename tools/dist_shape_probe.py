@@ -48,7 +48,7 @@ for it in range(12):
             timed('lru_undo', be.undo_bookkeeping)
         timed('scatter', lambda: be.scatter(gal, order, save_undo=not commit))
         timed('sweep_record', lambda: be.sweep_record(p, label, rec))
-        rec['all'].copy_(rec['own'].unsqueeze(0).expand(R, -1))
+        rec['all'].copy_(rec['own'].unsqueeze(0).expand(R, -1, -1))
         timed('finalize_gathered', lambda: be.finalize_gathered(p, label, rec, R))
         if not commit:
             timed('restore', be.restore_queue)

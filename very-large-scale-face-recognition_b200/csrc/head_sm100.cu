@@ -730,7 +730,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       asm volatile("bar.sync 2, 288;" ::: "memory");   // released by the MMA warp once every tcgen05.mma of the item has completed
       tc_fence_after();
       constexpr int half = D / 2;                  // D is a multiple of 64
-      float* dst = sw.o_part + ((int64_t)chunk * prm.n_rows + (row_ok ? row : 0)) * D + g * half;
+      // A TMEM lane is a row, so a thread holds 32 consecutive floats of ITS row: stored straight from the registers every store
+      // instruction touched 32 different 2 KB-strided rows, 16 bytes each (the write-out took 12-17 us per item, the CTA pair's
+      // largest fixed cost).  Each warp transposes its 32 x 32 block through 4.5 KB of the idle P~ buffers instead: a store
+      // instruction then covers 4 rows x 128 contiguous bytes.
+      float* stg = reinterpret_cast<float*>(sPt) + (warp - 4) * (32 * 36);
+      float* dst0 = sw.o_part + ((int64_t)chunk * prm.n_rows + row0 + q4 * 32) * D + g * half;
+      (void)row_ok;
       for (int c0 = 0; c0 < half; c0 += 32) {
         uint32_t v[32];
         if (n_tiles > 0) {
@@ -739,12 +745,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = 0u;
         }
-        if (row_ok) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            *reinterpret_cast<uint4*>(dst + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-          }
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
+          const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 36 + c);
+          if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c) = x;
         }
+        __syncwarp();
       }
       tc_fence_before();
     }
@@ -897,6 +907,22 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
       t1 = std::max(t1, h[i][7]);
     }
     fprintf(fo, "[sweep stamps] debug=%d %d CTAs, kernel %.1f us (globaltimer)\n", p.debug, 2 * n_items, (t1 - t0) * 1e-3);
+    // where an item's time goes (cycles, mean over the CTAs of each role): set-up (barriers, TMEM alloc, cluster sync) | until the
+    // MMA loop starts (P into TMEM / first W tile) | MMA loop | after the loop to the end of the role's work (O write-out, partial
+    // merge) | final cluster sync + dealloc
+    for (int role = 0; role < 2; ++role) {
+      double ph[5] = {0, 0, 0, 0, 0};
+      int cnt = 0;
+      for (int i = role; i < n; i += 2, ++cnt) {
+        ph[0] += (double)(h[i][1] - h[i][0]);
+        ph[1] += (double)(h[i][2] - h[i][1]);
+        ph[2] += (double)(h[i][3] - h[i][2]);
+        ph[3] += (double)(h[i][4] - h[i][3]);
+        ph[4] += (double)(h[i][5] - h[i][4]);
+      }
+      fprintf(fo, "  %s-CTA item phases (cycles): set-up %.0f | to MMA loop %.0f | MMA loop %.0f | tail work %.0f | final sync %.0f\n", role ? "O" : "S", ph[0] / cnt,
+              ph[1] / cnt, ph[2] / cnt, ph[3] / cnt, ph[4] / cnt);
+    }
     static long long hp[1024][8];
     cudaMemcpyFromSymbol(hp, g_sweep_prof, sizeof(hp));
     for (int role = 0; role < 2; ++role) {

@@ -364,7 +364,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     {
       constexpr int half = D / 2;
-      float* dst = sw.o_part + ((int64_t)chunk * prm.n_rows + (row_ok ? row : 0)) * D + g * half;
+      // each warp transposes its 32 x 32 block through 4.5 KB of the idle ring (beyond the 16 KB the scalar merge below uses), so
+      // that a store instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes (see head_sm100.cu)
+      float* stg = reinterpret_cast<float*>(sW + 16384) + (warp - 4) * (32 * 36);
+      float* dst0 = sw.o_part + ((int64_t)chunk * prm.n_rows + row0 + q4 * 32) * D + g * half;
 #pragma unroll 1
       for (int c0 = 0; c0 < half; c0 += 32) {
         uint32_t v[32];
@@ -374,10 +377,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
           for (int c = 0; c < 32; ++c) v[c] = 0u;
         }
-        if (row_ok) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) *reinterpret_cast<uint4*>(dst + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
+          const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 36 + c);
+          if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c) = x;
         }
+        __syncwarp();
       }
       tc_fence_before();
     }
