@@ -52,9 +52,11 @@ def peaks():
 
 def sweep_traffic(w, world):
     """DRAM bytes of one main-sweep launch from the committed ncu --set full capture (C3 at one GPU only)."""
-    p = os.path.join(ROOT, 'profiles', 'r1_sweep_traffic.json')
-    if world == 1 and w is WORKLOADS['c3'] and os.path.isfile(p):
-        return json.load(open(p))['dram_bytes_per_launch']
+    if world == 1 and w is WORKLOADS['c3']:
+        for name in ('r2_sweep_traffic.json', 'r1_sweep_traffic.json'):       # the newest capture of this kernel
+            p = os.path.join(ROOT, 'profiles', name)
+            if os.path.isfile(p):
+                return json.load(open(p))['dram_bytes_per_launch']
     return None
 
 
