@@ -1160,7 +1160,7 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
 static int run_one_sweep(ffc_head* h, SweepArgs a, int cache_slot, int stat_slot, int top_slot, const ffc_head_stats* out, int64_t idx_base,
                          const int32_t* idx_map, cudaStream_t s) {
   const bool bf16 = h->cfg.precision == FFC_PREC_BF16;
-  a.n_chunks = bf16 ? sm100_pick_chunks(a.n_rows, a.n_cols, a.D) : simt_pick_chunks(a.n_rows, a.n_cols);
+  a.n_chunks = bf16 ? sm100_pick_chunks(a.n_rows, a.n_cols, a.D, (int)std::min<int64_t>(h->part_rows_cap / std::max(1, a.n_rows), h->max_chunks)) : simt_pick_chunks(a.n_rows, a.n_cols);
   FFC_REQUIRE((int64_t)a.n_chunks * a.n_rows <= h->part_rows_cap && a.n_chunks <= h->max_chunks, "head sweep: partial workspace too small (%d chunks x %d rows)",
               a.n_chunks, a.n_rows);
   a.l_part = h->l_part;
@@ -1209,7 +1209,7 @@ static int run_merged_sweeps(ffc_head* h, SweepArgs a, const ffc_head_pass* in, 
       w.n_cols_dev = nullptr;
       w.tcol = h->tcol;
       w.cmask = in->cmask;
-      w.n_chunks = sm100_pick_chunks(n, w.n_cols, D);
+      w.n_chunks = sm100_pick_chunks(n, w.n_cols, D, (int)std::min<int64_t>(h->part_rows_cap / std::max(1, n) - 2, h->max_chunks));   // - the two side sweeps' partials
     } else {
       w.W_bf16 = h->side_bf16 + (int64_t)(i - 1) * c.max_rows * D;
       w.n_cols = c.max_rows;

@@ -49,7 +49,7 @@ void sm100_cache_destroy(Sm100Cache*);
 int launch_sweep_sm100(Sm100Cache* cache, int cache_slot, const SweepArgs& a, cudaStream_t s);
 // up to three sweeps that share the probe rows in ONE launch (main + the two side sweeps)
 int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps, cudaStream_t s);
-int sm100_pick_chunks(int n_rows, int64_t n_cols, int D);
+int sm100_pick_chunks(int n_rows, int64_t n_cols, int D, int chunk_cap);   // chunk_cap: most column chunks the partial workspace holds
 
 // sorted (descending) insertion into a k-entry list held in registers / local arrays
 template <int K>

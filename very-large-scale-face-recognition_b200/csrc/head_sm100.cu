@@ -34,18 +34,14 @@ namespace ffc {
 constexpr int BM = 128;            // probe rows per item
 constexpr int BN = 128;            // queue rows per tile
 constexpr int KC = 64;             // bf16 elements per 128-byte swizzle row
-#ifndef FFC_P_TMEM
-#define FFC_P_TMEM 1     // 1: the probe tile P is the TMEM A operand of GEMM-1 (tcgen05.mma TS form); 0: P resident in shared memory (SS form)
-#endif
 #ifndef FFC_NS1
-#define FFC_NS1 (FFC_P_TMEM ? 12 : 5)
+#define FFC_NS1 12
 #endif
 #ifndef FFC_JB
 #define FFC_JB 32
 #endif
 constexpr int NS1 = FFC_NS1;       // S-CTA W K-chunk stages (16 KB each)
-constexpr bool P_TMEM = FFC_P_TMEM != 0;
-constexpr int NSB = P_TMEM ? 2 : 4; // S accumulators in the S-CTA's TMEM (128 columns each); with P in TMEM: S0 S1 | P (D/2 columns at 256)
+constexpr int NSB = 2;             // S accumulators in the S-CTA's TMEM (128 columns each): S0 S1 | P (D/2 columns at 256)
 constexpr int P_TMEM_COL = 256;
 constexpr int NPB = 3;             // P~ buffers in the O-CTA's shared memory
 constexpr int JB = FFC_JB;         // queue rows per O-CTA W stage
@@ -55,25 +51,29 @@ constexpr int CHUNK1_BYTES = BN * KC * 2;   // 16384
 
 // ---- shared memory map (same for both roles; 1024-byte aligned base) ----
 // [0, 1024)                 barriers, tmem base
-// S-CTA: [1024, ...)        NS1 x 16 KB W chunk ring (K-major SW128), then 12 x 128 B top-k scan staging
-//                           (with FFC_P_TMEM=0 the P tile, D/64 x 16 KB, sits in front of the ring)
+// S-CTA: [1024, ...)        NS1 x 16 KB W chunk ring (K-major SW128), 12 x 128 B top-k scan staging, then the end-of-item staging of the
+//                           epilogue warpgroups' per-row partials ([2][128] denominators, [2][128][KMAX] top-k values and columns)
 // O-CTA: [1024, +96K)       P~ buffers 3 x 32 KB (interleaved K-major), then NS2 x (D/64 * 4 KB) W stage ring
 // ---- tensor memory (512 columns per SM) ----
 // S-CTA: [0, 256) two S accumulators, [256, 256 + D/2) the probe tile P as packed bf16 pairs (lane = row)
 // O-CTA: [0, D) the fp32 gradient accumulator O
 constexpr int OFF_DATA = 1024;
 constexpr int PT_BYTES = BM * BN * 2;       // 32768 per P~ buffer
+constexpr int SCAN_STAGE_BYTES = NEPI * 4 * 128;
+constexpr int ITEM_STAGE_BYTES = (NEPI - 1) * BM * (4 + 8 * KMAX);
 
 struct Bars {   // all in the first 1024 bytes
-  uint64_t p_full;
+  uint64_t p_full;                 // the item's probe tile is in TMEM (12 epilogue warps arrive, once per item)
   uint64_t w_full[NS1], w_empty[NS1];
   uint64_t s_full[NEPI];           // one per epilogue warpgroup (NOT per S buffer): each is waited by one warpgroup, in order
   uint64_t s_empty[NSB];
-  uint64_t pt_empty[NPB];          // S-CTA side: P~ buffer b may be overwritten (signalled by the peer's tcgen05.commit)
+  uint64_t pt_empty[NPB];          // S-CTA side: P~ buffer b may be overwritten (signalled by the peer's tcgen05.commit, or by its O
+                                   // write-out warps for the buffer they used as staging)
   uint64_t w2_full[8], w2_empty[8];
   uint64_t pt_full[NPB];           // O-CTA side: P~ buffer b is complete (st.async complete_tx, 32 KB per tile)
   uint64_t pt_ready[NPB];          // O-CTA side: ... and the proxy fence that lets tcgen05.mma read it has been executed
-  uint64_t o_full;
+  uint64_t o_full;                 // O-CTA: every tcgen05.mma of the item has completed (O may be read)
+  uint64_t o_empty;                // O-CTA: the item's O has been read out of TMEM (the next item may overwrite it)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -90,7 +90,7 @@ __device__ __forceinline__ uint32_t pt_offset(uint32_t piece, uint32_t r) { retu
 #endif
 
 #if FFC_SM100_DEBUG_BUILD
-// per-CTA phase stamps of the last launch: [cta][0..5] = clock64 at start / set-up done / MMA loop start / MMA loop end /
+// per-CTA phase stamps of the last launch: [cta][0..5] = clock64 at start / set-up done / first MMA loop start / last MMA loop end /
 // role work done / after the final cluster sync; [6], [7] = globaltimer (ns) at start / end
 __device__ long long g_sweep_stamps[1024][8];
 #define FFC_STAMP(slot)                                                                    \
@@ -105,7 +105,7 @@ __device__ long long g_sweep_stamps[1024][8];
   } while (0)
 // per-CTA cycle sums: [0] MMA warp waiting for its accumulator / P~ buffer, [1] MMA warp waiting for W (TMA), [2] MMA warp
 // issuing, [3] epilogue warp 4 waiting for S, [4] epilogue warp 4 waiting for a free P~ buffer, [5] epilogue warp 4 working,
-// [6] TMA producer waiting for a free stage
+// [6] TMA producer waiting for a free stage, [7] S-CTA: top-k scan triggers; O-CTA: MMA warp between two items (O read-out)
 __device__ long long g_sweep_prof[1024][8];
 #define FFC_PROF_DECL(name) long long name = 0
 #define FFC_PROF_T(var) const long long var = clock64()
@@ -131,11 +131,34 @@ struct SweepShape {
   static constexpr int NS2 = NS2_RAW > 8 ? 8 : (NS2_RAW < 2 ? 2 : NS2_RAW);
   static constexpr int N2 = D < 256 ? D : 256;               // GEMM-2 instruction N
   static constexpr int NHALF = (D + 255) / 256;              // GEMM-2 instructions per K step
-  static constexpr size_t SMEM_S = OFF_DATA + (P_TMEM ? 0 : (size_t)NKC * CHUNK1_BYTES) + (size_t)NS1 * CHUNK1_BYTES + NEPI * 4 * 128;   // + top-k scan staging
+  static constexpr size_t SMEM_S = OFF_DATA + (size_t)NS1 * CHUNK1_BYTES + SCAN_STAGE_BYTES + ITEM_STAGE_BYTES;
   static constexpr size_t SMEM_O = OFF_DATA + NPB * (size_t)PT_BYTES + (size_t)NS2 * STAGE2_BYTES;
   static constexpr size_t SMEM = (SMEM_S > SMEM_O ? SMEM_S : SMEM_O) + 1024;   // slack for the 1024-byte alignment of the base
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
+
+// A work item = (sub-sweep, row tile, column chunk).  Items are numbered [sub-sweep][column chunk][row tile fastest]; a CTA pair
+// works through items pair, pair + n_pairs, ... (every role of both CTAs decodes the same sequence on its own).
+struct Item {
+  int sidx, chunk, row0, t_begin, n_tiles;
+  int64_t n_cols;
+};
+__device__ __forceinline__ Item decode_item(const Sm100Params& prm, int item_all) {
+  Item it;
+  it.sidx = item_all >= prm.sub[2].item0 ? 2 : (item_all >= prm.sub[1].item0 ? 1 : 0);
+  const SubSweep& sw = prm.sub[it.sidx];
+  const int item = item_all - sw.item0;
+  const int n_row_tiles = (prm.n_rows + BM - 1) / BM;
+  it.chunk = item / n_row_tiles;
+  it.row0 = (item - it.chunk * n_row_tiles) * BM;
+  it.n_cols = sw.n_cols_dev ? (int64_t)*sw.n_cols_dev : sw.n_cols;
+  const int n_tiles_total = (int)((it.n_cols + BN - 1) / BN);
+  it.t_begin = it.chunk * sw.tiles_per_chunk;
+  int t_end = it.t_begin + sw.tiles_per_chunk;
+  if (t_end > n_tiles_total) t_end = n_tiles_total;
+  it.n_tiles = t_end > it.t_begin ? t_end - it.t_begin : 0;
+  return it;
+}
 
 template <bool SV, int D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
@@ -151,35 +174,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   Bars& bars = *reinterpret_cast<Bars*>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int item_all = blockIdx.x >> 1;
-  const int sidx = item_all >= prm.sub[2].item0 ? 2 : (item_all >= prm.sub[1].item0 ? 1 : 0);
-  const SubSweep& sw = prm.sub[sidx];
-  const CUtensorMap* map_w1 = sidx == 0 ? &map_w1a : (sidx == 1 ? &map_w1b : &map_w1c);
-  const CUtensorMap* map_w2 = sidx == 0 ? &map_w2a : (sidx == 1 ? &map_w2b : &map_w2c);
-  const int item = item_all - sw.item0;
-  const int n_row_tiles = (prm.n_rows + BM - 1) / BM;
-  const int rt = item % n_row_tiles, chunk = item / n_row_tiles;
-  const int row0 = rt * BM;
-  const int64_t n_cols = sw.n_cols_dev ? (int64_t)*sw.n_cols_dev : sw.n_cols;
-  const int n_tiles_total = (int)((n_cols + BN - 1) / BN);
-  const int t_begin = chunk * sw.tiles_per_chunk;
-  int t_end = t_begin + sw.tiles_per_chunk;
-  if (t_end > n_tiles_total) t_end = n_tiles_total;
-  const int n_tiles = t_end > t_begin ? t_end - t_begin : 0;
+  // Item loop: pair p works through items p, p + n_pairs, ...  The default launch has one pair per item (the loop runs once and the
+  // hardware deals the items to the SMs); a persistent launch (see persistent_grid) has fewer pairs than items.  Barriers, tensor
+  // memory and the pipeline rings are set up once and their phases run on across items, so between two items only the data
+  // dependencies remain: the S-CTA reloads P once the item's last GEMM-1 has completed, the O-CTA's next item starts once O has been
+  // read out of TMEM -- while the W rings are already being refilled and the S-CTA works two P~ tiles ahead.
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_items = prm.n_items;
   const int dbg = FFC_SM100_DEBUG_BUILD ? prm.debug : 0;
   const bool dbg_noO = (dbg & 1) != 0, dbg_noEpi = (dbg & 2) != 0, dbg_noS = (dbg & 4) != 0, dbg_noHand = (dbg & 16) != 0, dbg_noTma = (dbg & 64) != 0;
+  (void)map_p;
 
   if (threadIdx.x == 0) {
     FFC_STAMP(0);
     FFC_STAMP_NS(6);
   }
-  unsigned char* sP = smem + OFF_DATA;                         // S-CTA
-  unsigned char* sW1 = sP + (P_TMEM ? 0 : NKC * CHUNK1_BYTES);   // S-CTA (P lives in TMEM when P_TMEM)
+  unsigned char* sW1 = smem + OFF_DATA;                        // S-CTA (P lives in TMEM)
   unsigned char* sPt = smem + OFF_DATA;                        // O-CTA
   unsigned char* sW2 = sPt + NPB * PT_BYTES;                   // O-CTA
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars.p_full, P_TMEM ? 4 : 1);
+    mbar_init(&bars.p_full, 4 * NEPI);
     for (int i = 0; i < NS1; ++i) {
       mbar_init(&bars.w_full[i], 1);
       mbar_init(&bars.w_empty[i], 1);
@@ -196,10 +211,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       mbar_init(&bars.w2_empty[i], 1);
     }
     mbar_init(&bars.o_full, 1);
+    mbar_init(&bars.o_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    // S-CTA: NSB x 128 columns of S; O-CTA: D columns of O (power of two >= 32)
+    // S-CTA: NSB x 128 columns of S + P; O-CTA: D columns of O (power of two >= 32)
     const uint32_t ncols = rank == 0 ? 512u : (uint32_t)(D < 32 ? 32 : D);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -213,20 +229,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
   if (rank == 0) {
     // =========================================== S-CTA ===========================================
     if (warp == 0) {
-      // ---- TMA producer (converged warp, one elected lane issues) ----
-      if (n_tiles > 0 && !dbg_noS) {
-        if (!P_TMEM) {
-          if (elect_one()) {
-            mbar_expect_tx(&bars.p_full, (uint32_t)(NKC * CHUNK1_BYTES));
-#pragma unroll
-            for (int kc = 0; kc < NKC; ++kc) tma_load_2d(&map_p, &bars.p_full, sP + kc * CHUNK1_BYTES, kc * KC, row0);
-          }
-          __syncwarp();
-        }
-        int stage = 0;
-        uint32_t ph = 0;
-        FFC_PROF_DECL(prof_tma);
-        for (int t = t_begin; t < t_end && !dbg_noTma; ++t) {
+      // ---- TMA producer (converged warp, one elected lane issues); runs ahead into the next item as far as the ring allows ----
+      int stage = 0;
+      uint32_t ph = 0;
+      FFC_PROF_DECL(prof_tma);
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        if (it.n_tiles == 0 || dbg_noS || dbg_noTma) continue;
+        const CUtensorMap* map_w1 = it.sidx == 0 ? &map_w1a : (it.sidx == 1 ? &map_w1b : &map_w1c);
+        for (int t = it.t_begin; t < it.t_begin + it.n_tiles; ++t) {
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
             FFC_PROF_T(q0);
@@ -244,27 +255,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             }
           }
         }
-        if (lane == 0) FFC_PROF_STORE(6, prof_tma);
       }
+      if (lane == 0) FFC_PROF_STORE(6, prof_tma);
     } else if (warp == 1) {
       // ---- GEMM-1 issue: S[128 x 128] = P[128 x D] . W_tile[128 x D]^T, 4 x (K = 16) per 64-column chunk ----
-      if (n_tiles > 0) {
-        constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-        if (!dbg_noS) mbar_wait(&bars.p_full, 0);
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      const uint64_t b0 = make_desc(smem_u32(sW1), 16, 1024);
+      int stage = 0;
+      uint32_t ph = 0;
+      uint32_t gi = 0;      // tiles issued by this CTA so far (all items): tile gi uses S buffer gi % NSB and epilogue warpgroup gi % NEPI
+      int wg = 0;
+      uint32_t ni = 0;      // items with tiles so far
+      bool stamped = false;
+      FFC_PROF_DECL(prof_a);
+      FFC_PROF_DECL(prof_b);
+      FFC_PROF_DECL(prof_c);
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        if (it.n_tiles == 0) continue;
+        if (!dbg_noS) mbar_wait(&bars.p_full, ni & 1);       // the item's probe tile is in TMEM
         tc_fence_after();
-        const uint64_t a0 = make_desc(smem_u32(sP), 16, 1024);
-        const uint64_t b0 = make_desc(smem_u32(sW1), 16, 1024);
-        int stage = 0;
-        uint32_t ph = 0;
-        if (lane == 0) FFC_STAMP(2);
-        FFC_PROF_DECL(prof_a);
-        FFC_PROF_DECL(prof_b);
-        FFC_PROF_DECL(prof_c);
-        int wg = 0;      // epilogue warpgroup of tile i (i % NEPI): its s_full barrier is signalled
-        for (int i = 0; i < n_tiles; ++i, wg = (wg + 1 == NEPI ? 0 : wg + 1)) {
-          const int sb = i & (NSB - 1);
+        if (!stamped && lane == 0) FFC_STAMP(2);
+        stamped = true;
+        for (int i = 0; i < it.n_tiles; ++i, ++gi, wg = (wg + 1 == NEPI ? 0 : wg + 1)) {
+          const int sb = (int)(gi & (NSB - 1));
           FFC_PROF_T(q0);
-          mbar_wait(&bars.s_empty[sb], ((uint32_t)(i / NSB) & 1) ^ 1);
+          mbar_wait(&bars.s_empty[sb], ((gi / NSB) & 1) ^ 1);
           tc_fence_after();
           FFC_PROF_T(q1);
           FFC_PROF_ADD(prof_a, q0, q1);
@@ -285,16 +301,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             FFC_PROF_ADD(prof_b, q2, q3);
             if (elect_one()) {
               const uint64_t bd = b0 + (uint64_t)(stage * (CHUNK1_BYTES >> 4));
-              if (P_TMEM) {
-                // A = P[128 x 16] from TMEM: lane = probe row, 8 columns (two bf16 per column) per K = 16 step
-                const uint32_t ta = tmem_base + (uint32_t)(P_TMEM_COL + kc * (KC / 2));
+              // A = P[128 x 16] from TMEM: lane = probe row, 8 columns (two bf16 per column) per K = 16 step
+              const uint32_t ta = tmem_base + (uint32_t)(P_TMEM_COL + kc * (KC / 2));
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) tc_mma_ts(tmem_s, ta + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-              } else {
-                const uint64_t ad = a0 + (uint64_t)(kc * (CHUNK1_BYTES >> 4));
-#pragma unroll
-                for (int k = 0; k < KC / 16; ++k) tc_mma(tmem_s, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-              }
+              for (int k = 0; k < KC / 16; ++k) tc_mma_ts(tmem_s, ta + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
               if (!dbg_noTma) tc_commit(&bars.w_empty[stage]);
               if (kc == NKC - 1) tc_commit(&bars.s_full[wg]);
             }
@@ -307,229 +317,310 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             }
           }
         }
-        if (lane == 0) {
-          FFC_STAMP(3);
-          FFC_PROF_STORE(0, prof_a);
-          FFC_PROF_STORE(1, prof_b);
-          FFC_PROF_STORE(2, prof_c);
-        }
+        ++ni;
+        if (lane == 0) FFC_STAMP(3);
+      }
+      if (lane == 0) {
+        FFC_PROF_STORE(0, prof_a);
+        FFC_PROF_STORE(1, prof_b);
+        FFC_PROF_STORE(2, prof_c);
       }
     } else if (warp >= 4) {
-      // ---- epilogue: warpgroup g takes the tiles of parity g (S buffer i%4, P~ buffer i%3) ----
+      // ---- epilogue: warpgroup g takes the CTA's tiles gi with gi % NEPI == g (S buffer gi % NSB, P~ buffer gi % NPB == g) ----
       const int g = (warp - 4) >> 2;
       const int q4 = warp & 3;                    // TMEM lane quarter
       const int r_local = q4 * 32 + lane;         // row within the item
-      const int row = row0 + r_local;
-      const bool row_ok = row < prm.n_rows;
-      const int32_t tcol = (row_ok && sw.tcol) ? sw.tcol[row] : -1;
-      const bool outl = row_ok && prm.is_out && prm.is_out[row];
-      const bool warp_out = __any_sync(0xffffffffu, outl);
-      float thr = INFINITY;
-      if (SV && row_ok && sw.thr) thr = sw.thr[row];
       const float a2 = prm.a2, b2 = prm.b2;
       const int k = prm.k;
-      float lsum = 0.f;
-      // hard-negative top-k state of this row (see topk_scan16)
-      int tk[KMAX], tc[KMAX];
-#pragma unroll
-      for (int q = 0; q < KMAX; ++q) {
-        tk[q] = 0;
-        tc[q] = -1;
-      }
-      int kth = 0;
-      // Threshold shared by the work items of the same probe rows (one per column chunk): the k-th largest cosine any of them
-      // has seen so far is a lower bound of the row's final k-th, so nothing at or below it can enter the merged top-k.  Each
-      // item publishes its own k-th (atomicMax on the integer key) and picks the maximum up at every tile: the candidate rate
-      // of an item falls as if it had seen all chunks' columns.  Main sweep only (the side sets merge per loss).
       uint32_t* scan_stage = reinterpret_cast<uint32_t*>(sW1 + NS1 * CHUNK1_BYTES) + (warp - 4) * 32;   // 128 bytes per epilogue warp
-      int32_t* kshare = (sidx == 0 && outl) ? prm.kth_shared + row : nullptr;
-      int kfloor = 0, kpub = 0;
-      float pthr = __uint_as_float(__float_as_uint(ex2f(-b2)) & 0xffff0000u);    // p~ of cosine 0, rounded down to bf16
+      // end-of-item staging of warpgroups 1 and 2 (own region: the W ring is being refilled for the next item by then)
+      unsigned char* item_stage = sW1 + NS1 * CHUNK1_BYTES + SCAN_STAGE_BYTES;
+      float* stage_l = reinterpret_cast<float*>(item_stage);                                           // [2][128]
+      float* stage_v = reinterpret_cast<float*>(item_stage + (NEPI - 1) * BM * 4);                     // [2][128][KMAX]
+      int32_t* stage_i = reinterpret_cast<int32_t*>(item_stage + (NEPI - 1) * BM * 4 * (1 + KMAX));    // [2][128][KMAX]
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
-      // tile i uses S buffer i % NSB and P~ buffer i % NPB; NEPI == NPB, so this warpgroup always writes P~ buffer g
+      // tile gi uses S buffer gi % NSB and P~ buffer gi % NPB; NEPI == NPB, so this warpgroup always writes P~ buffer g
       static_assert(NEPI == NPB, "epilogue warpgroups and P~ buffers are paired");
       const int pb = g;
-      uint32_t pt_use = 0;
-      if (P_TMEM && g == 0 && n_tiles > 0 && !dbg_noS) {
-        // probe tile -> TMEM (the A operand of every GEMM-1 of this item): thread = row, 32 columns (64 bf16, 128 bytes) per store
-        const uint4* src = reinterpret_cast<const uint4*>(prm.p16 + (int64_t)(row_ok ? row : 0) * D);
-        const uint32_t tp = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)P_TMEM_COL;
-#pragma unroll 1
-        for (int c0 = 0; c0 < D / 2; c0 += 32) {
-          uint32_t v[32];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint4 t = row_ok ? __ldg(src + c0 / 4 + q) : make_uint4(0u, 0u, 0u, 0u);
-            v[4 * q] = t.x;
-            v[4 * q + 1] = t.y;
-            v[4 * q + 2] = t.z;
-            v[4 * q + 3] = t.w;
-          }
-          tc_st32(tp + (uint32_t)c0, v);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.p_full);
-      }
+      uint32_t pt_use = 0;      // tiles this warpgroup has taken so far (all items): phase of s_full[g] / pt_empty[g]
+      uint32_t gi0 = 0;         // the CTA's tile count at the start of the current item
       FFC_PROF_DECL(prof_e0);
       FFC_PROF_DECL(prof_e1);
       FFC_PROF_DECL(prof_e2);
       FFC_PROF_DECL(prof_trig);
-      for (int i = g; i < n_tiles; i += NEPI, ++pt_use) {
-        const int sb = i & (NSB - 1);
-        const int j0 = (t_begin + i) * BN;
-        // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
-        uint4 cm = make_uint4(0u, 0u, 0u, 0u);
-        if (sw.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(sw.cmask + (j0 >> 5)));
-        int kshared = 0;
-        if (kshare) kshared = __ldcg(kshare);
-        FFC_PROF_T(e0);
-        // s_full is per warpgroup: tile i is this warpgroup's pt_use-th tile.  (Per-buffer barriers would be waited by
-        // different warpgroups in turn; with fewer S buffers than warpgroups + 1 a slow warpgroup gets lapped by a phase and
-        // a parity wait two phases behind never returns.)
-        mbar_wait(&bars.s_full[g], pt_use & 1);
-        tc_fence_after();
-        FFC_PROF_T(e1);
-        if (!dbg_noHand) mbar_wait(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
-        FFC_PROF_T(e2);
-        FFC_PROF_ADD(prof_e0, e0, e1);
-        FFC_PROF_ADD(prof_e1, e1, e2);
-        const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
-        const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
-        const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
-        // One loop over the tile's four 32-column chunks.  Exclusions (a `ones` column, the row's target, the ragged tail) are
-        // decided per CHUNK and warp-uniformly: only chunks that hold one pay for the per-element test, the others are pure
-        // ld -> ex2 -> pack -> st.async.  (At 8-way shard shapes ~60 % of the TILES hold a `ones` column, but only ~20 % of
-        // the chunks.)
-        kfloor = max(kfloor, kshared);
-        kth = max(kth, kfloor);
-        if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
-        float l0 = 0.f, l1 = 0.f;
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        const SubSweep& sw = prm.sub[it.sidx];
+        const int sidx = it.sidx, chunk = it.chunk, row0 = it.row0, t_begin = it.t_begin, n_tiles = it.n_tiles;
+        const int64_t n_cols = it.n_cols;
+        const int row = row0 + r_local;
+        const bool row_ok = row < prm.n_rows;
+        if (n_tiles == 0) {
+          // an item without columns still owes its l / top-k partials (zeros / -inf)
+          if (g == 0 && row_ok) {
+            const int64_t pr = (int64_t)chunk * prm.n_rows + row;
+            sw.l_part[pr] = 0.f;
+            for (int q = 0; q < k; ++q) {
+              sw.topv_part[pr * k + q] = -INFINITY;
+              sw.topi_part[pr * k + q] = -1;
+            }
+          }
+          continue;
+        }
+        const int32_t tcol = (row_ok && sw.tcol) ? sw.tcol[row] : -1;
+        const bool outl = row_ok && prm.is_out && prm.is_out[row];
+        const bool warp_out = __any_sync(0xffffffffu, outl);
+        float thr = INFINITY;
+        if (SV && row_ok && sw.thr) thr = sw.thr[row];
+        float lsum = 0.f;
+        // hard-negative top-k state of this row (see topk_scan16)
+        int tk[KMAX], tc[KMAX];
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+          tk[q] = 0;
+          tc[q] = -1;
+        }
+        int kth = 0;
+        // Threshold shared by the work items of the same probe rows (one per column chunk): the k-th largest cosine any of them
+        // has seen so far is a lower bound of the row's final k-th, so nothing at or below it can enter the merged top-k.  Each
+        // item publishes its own k-th (atomicMax on the integer key) and picks the maximum up at every tile: the candidate rate
+        // of an item falls as if it had seen all chunks' columns.  Main sweep only (the side sets merge per loss).
+        int32_t* kshare = (sidx == 0 && outl) ? prm.kth_shared + row : nullptr;
+        int kfloor = 0, kpub = 0;
+        float pthr = __uint_as_float(__float_as_uint(ex2f(-b2)) & 0xffff0000u);    // p~ of cosine 0, rounded down to bf16
+        if (!dbg_noS) {
+          // probe tile -> TMEM (the A operand of every GEMM-1 of this item): thread = row, 32 columns (64 bf16, 128 bytes) per store; the
+          // three warpgroups take the 32-column pieces round-robin.  Every GEMM-1 of the previous item has completed: its epilogue
+          // warps met at the end-of-item barrier after their last s_full.
+          const uint4* src = reinterpret_cast<const uint4*>(prm.p16 + (int64_t)(row_ok ? row : 0) * D);
+          const uint32_t tp = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)P_TMEM_COL;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t v[32];
-          if (dbg_noEpi) {
+          for (int c0 = 32 * g; c0 < D / 2; c0 += 32 * NEPI) {
+            uint32_t v[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = 0u;
-          } else {
-            tc_ld32(tmem_s + cc * 32, v);
+            for (int q = 0; q < 8; ++q) {
+              const uint4 t = row_ok ? __ldg(src + c0 / 4 + q) : make_uint4(0u, 0u, 0u, 0u);
+              v[4 * q] = t.x;
+              v[4 * q + 1] = t.y;
+              v[4 * q + 2] = t.z;
+              v[4 * q + 3] = t.w;
+            }
+            tc_st32(tp + (uint32_t)c0, v);
           }
-          if (cc == BN / 32 - 1) {      // S buffer sb is in registers now: a later tile's MMA may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
-          }
-          const int col0 = j0 + cc * 32;
-          uint32_t excl = cc == 0 ? cm.x : cc == 1 ? cm.y : cc == 2 ? cm.z : cm.w;
-          const int trel = tcol - col0;
-          if ((unsigned)trel < 32u) excl |= 1u << trel;
-          if ((int64_t)col0 + 32 > n_cols) {
-            const int nv = (int)(n_cols - col0);   // valid columns in this chunk (may be <= 0)
-            excl |= nv <= 0 ? 0xffffffffu : (0xffffffffu << nv);
-          }
-          const bool slow = __any_sync(0xffffffffu, excl != 0u);
-          uint32_t pk[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.p_full);
+        }
+        const int first = (g + NEPI - (int)(gi0 % NEPI)) % NEPI;      // this warpgroup's first tile of the item
+        for (int i = first; i < n_tiles; i += NEPI, ++pt_use) {
+          const int sb = (int)((gi0 + (uint32_t)i) & (NSB - 1));
+          const int j0 = (t_begin + i) * BN;
+          // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
+          uint4 cm = make_uint4(0u, 0u, 0u, 0u);
+          if (sw.cmask && (int64_t)j0 < n_cols) cm = __ldg(reinterpret_cast<const uint4*>(sw.cmask + (j0 >> 5)));
+          int kshared = 0;
+          if (kshare) kshared = __ldcg(kshare);
+          FFC_PROF_T(e0);
+          // s_full is per warpgroup: this is the warpgroup's pt_use-th tile.  (Per-buffer barriers would be waited by
+          // different warpgroups in turn; with fewer S buffers than warpgroups + 1 a slow warpgroup gets lapped by a phase and
+          // a parity wait two phases behind never returns.)
+          mbar_wait(&bars.s_full[g], pt_use & 1);
+          tc_fence_after();
+          FFC_PROF_T(e1);
+          if (!dbg_noHand) mbar_wait_cluster(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
+          FFC_PROF_T(e2);
+          FFC_PROF_ADD(prof_e0, e0, e1);
+          FFC_PROF_ADD(prof_e1, e1, e2);
+          const uint32_t tmem_s = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(sb * BN);
+          const uint32_t pt_remote = pt_remote0 + (uint32_t)(pb * PT_BYTES);
+          const uint32_t ptfull_remote = ptfull_remote0 + (uint32_t)(pb * 8);
+          // One loop over the tile's four 32-column chunks.  Exclusions (a `ones` column, the row's target, the ragged tail) are
+          // decided per CHUNK and warp-uniformly: only chunks that hold one pay for the per-element test, the others are pure
+          // ld -> ex2 -> pack -> st.async.  (At 8-way shard shapes ~60 % of the TILES hold a `ones` column, but only ~20 % of
+          // the chunks.)
+          kfloor = max(kfloor, kshared);
+          kth = max(kth, kfloor);
+          if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+          for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t v[32];
             if (dbg_noEpi) {
-              pk[c >> 1] = 0u;
-              continue;
-            }
-            const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
-            float p0, p1, g0, g1;
-            if (SV) {
-              const bool m0 = x0 > thr, m1 = x1 > thr;
-              p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
-              p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
-              g0 = m0 ? p0 * SV_T : p0;
-              g1 = m1 ? p1 * SV_T : p1;
-            } else {
-              p0 = g0 = ex2f(fmaf(x0, a2, -b2));
-              p1 = g1 = ex2f(fmaf(x1, a2, -b2));
-            }
-            if (slow) {   // warp-uniform: only chunks that contain an excluded column pay for the per-element test
-              if ((excl >> c) & 1u) p0 = g0 = 0.f;
-              if ((excl >> (c + 1)) & 1u) p1 = g1 = 0.f;
-            }
-            l0 += p0;
-            l1 += p1;
-            pk[c >> 1] = pack_bf16(g0, g1);
-          }
-          // ---- hard-negative top-k on the raw cosines of outlier rows ----
-          if (SV) {
-            if (warp_out) {
-              topk_scan16<0, 32>(v, excl & 0xffffu, col0, outl, k, tk, tc, kth, kfloor);
-              topk_scan16<16, 32>(v, excl >> 16, col0 + 16, outl, k, tk, tc, kth, kfloor);
-            }
-          } else if (warp_out) {
-            // Without SV, p~ is monotonic in the cosine: the chunk can only hold a candidate if the maximum of its packed p~ (one
-            // bf16x2 max tree; excluded columns are 0) reaches the row's threshold mapped to p~ space.
-            uint32_t m = pk[0];
 #pragma unroll
-            for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
-            const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
-            unsigned cand = __ballot_sync(0xffffffffu, outl && mf >= pthr);
-            if (cand) {
-              FFC_PROF_ADD(prof_trig, 0, 1);
-              if (__popc(cand) > 4) {      // many rows at once (the first tiles of an item): the per-lane scan is cheaper
+              for (int c = 0; c < 32; ++c) v[c] = 0u;
+            } else {
+              tc_ld32(tmem_s + cc * 32, v);
+            }
+            if (cc == BN / 32 - 1) {      // S buffer sb is in registers now: a later tile's MMA may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars.s_empty[sb]);
+            }
+            const int col0 = j0 + cc * 32;
+            uint32_t excl = cc == 0 ? cm.x : cc == 1 ? cm.y : cc == 2 ? cm.z : cm.w;
+            const int trel = tcol - col0;
+            if ((unsigned)trel < 32u) excl |= 1u << trel;
+            if ((int64_t)col0 + 32 > n_cols) {
+              const int nv = (int)(n_cols - col0);   // valid columns in this chunk (may be <= 0)
+              excl |= nv <= 0 ? 0xffffffffu : (0xffffffffu << nv);
+            }
+            const bool slow = __any_sync(0xffffffffu, excl != 0u);
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              if (dbg_noEpi) {
+                pk[c >> 1] = 0u;
+                continue;
+              }
+              const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
+              float p0, p1, g0, g1;
+              if (SV) {
+                const bool m0 = x0 > thr, m1 = x1 > thr;
+                p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
+                p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
+                g0 = m0 ? p0 * SV_T : p0;
+                g1 = m1 ? p1 * SV_T : p1;
+              } else {
+                p0 = g0 = ex2f(fmaf(x0, a2, -b2));
+                p1 = g1 = ex2f(fmaf(x1, a2, -b2));
+              }
+              if (slow) {   // warp-uniform: only chunks that contain an excluded column pay for the per-element test
+                if ((excl >> c) & 1u) p0 = g0 = 0.f;
+                if ((excl >> (c + 1)) & 1u) p1 = g1 = 0.f;
+              }
+              l0 += p0;
+              l1 += p1;
+              pk[c >> 1] = pack_bf16(g0, g1);
+            }
+            // ---- hard-negative top-k on the raw cosines of outlier rows ----
+            if (SV) {
+              if (warp_out) {
                 topk_scan16<0, 32>(v, excl & 0xffffu, col0, outl, k, tk, tc, kth, kfloor);
                 topk_scan16<16, 32>(v, excl >> 16, col0 + 16, outl, k, tk, tc, kth, kfloor);
-                cand = 0u;
               }
-              // Usually ONE lane (row) has a candidate: its 32 cosines go through shared memory so that the 32 lanes test one
-              // column each; the row's lane then inserts the (usually single) hit.  ~40 instructions instead of a 32-key scan.
-              while (cand) {
-                const int L = __ffs(cand) - 1;
-                cand &= cand - 1;
-                if (lane == L) {
+            } else if (warp_out) {
+              // Without SV, p~ is monotonic in the cosine: the chunk can only hold a candidate if the maximum of its packed p~ (one
+              // bf16x2 max tree; excluded columns are 0) reaches the row's threshold mapped to p~ space.
+              uint32_t m = pk[0];
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scan_stage + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
+              const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
+              unsigned cand = __ballot_sync(0xffffffffu, outl && mf >= pthr);
+              if (cand) {
+                FFC_PROF_ADD(prof_trig, 0, 1);
+                if (__popc(cand) > 4) {      // many rows at once (the first tiles of an item): the per-lane scan is cheaper
+                  topk_scan16<0, 32>(v, excl & 0xffffu, col0, outl, k, tk, tc, kth, kfloor);
+                  topk_scan16<16, 32>(v, excl >> 16, col0 + 16, outl, k, tk, tc, kth, kfloor);
+                  cand = 0u;
                 }
-                __syncwarp();
-                const uint32_t exclL = __shfl_sync(0xffffffffu, excl, L);
-                const int key = ((exclL >> lane) & 1u) ? 0 : (int)((scan_stage[lane] & TOPK_VAL_MASK) | (uint32_t)lane);
-                const int kthL = __shfl_sync(0xffffffffu, kth, L);
-                unsigned hits = __ballot_sync(0xffffffffu, key > kthL);
-                while (hits) {
-                  const int c = __ffs(hits) - 1;
-                  hits &= hits - 1;
-                  const int kc = __shfl_sync(0xffffffffu, key, c);
-                  if (lane == L && kc > kth) {
-                    topk_insert_key(kc, col0, k, tk, tc);
+                // Usually ONE lane (row) has a candidate: its 32 cosines go through shared memory so that the 32 lanes test one
+                // column each; the row's lane then inserts the (usually single) hit.  ~40 instructions instead of a 32-key scan.
+                while (cand) {
+                  const int L = __ffs(cand) - 1;
+                  cand &= cand - 1;
+                  if (lane == L) {
 #pragma unroll
-                    for (int r = 0; r < KMAX; ++r)
-                      if (r == k - 1) kth = max(tk[r], kfloor);
+                    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(scan_stage + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                   }
+                  __syncwarp();
+                  const uint32_t exclL = __shfl_sync(0xffffffffu, excl, L);
+                  const int key = ((exclL >> lane) & 1u) ? 0 : (int)((scan_stage[lane] & TOPK_VAL_MASK) | (uint32_t)lane);
+                  const int kthL = __shfl_sync(0xffffffffu, kth, L);
+                  unsigned hits = __ballot_sync(0xffffffffu, key > kthL);
+                  while (hits) {
+                    const int c = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int kc = __shfl_sync(0xffffffffu, key, c);
+                    if (lane == L && kc > kth) {
+                      topk_insert_key(kc, col0, k, tk, tc);
+#pragma unroll
+                      for (int r = 0; r < KMAX; ++r)
+                        if (r == k - 1) kth = max(tk[r], kfloor);
+                    }
+                  }
+                  __syncwarp();
                 }
-                __syncwarp();
+                // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
+                pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
               }
-              // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
-              pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+            }
+            // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
+            if (!dbg_noHand) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 4 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
+                            pk[4 * q + 3]);
             }
           }
-          // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
-          if (!dbg_noHand) {
+          lsum += l0 + l1;
+          if (kshare) {      // publish this item's own k-th when it has risen
+            int kown = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 4 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
-                          pk[4 * q + 3]);
+            for (int r = 0; r < KMAX; ++r)
+              if (r == k - 1) kown = tk[r];
+            if (kown > kpub) {
+              atomicMax(kshare, kown);
+              kpub = kown;
+            }
+          }
+          FFC_PROF_T(e3);
+          FFC_PROF_ADD(prof_e2, e2, e3);
+        }
+        gi0 += (uint32_t)n_tiles;
+        // ---- per-row partials: combine the three warpgroups through shared memory ----
+        // Named barrier 1 (the 12 epilogue warps): every warpgroup has seen its last s_full of the item, i.e. every GEMM-1 that reads
+        // this item's P has completed (the next item's P may be stored), and the previous item's staging has been consumed.
+        asm volatile("bar.sync 1, 384;" ::: "memory");
+        float tv[KMAX];
+        int32_t ti[KMAX];
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+          const bool live = tk[q] > 0;
+          tv[q] = live ? __int_as_float(tk[q] & (int)TOPK_VAL_MASK) : -INFINITY;
+          ti[q] = live ? tc[q] + (tk[q] & 31) : -1;
+        }
+        if (g >= 1) {
+          stage_l[(g - 1) * BM + r_local] = lsum;
+#pragma unroll
+          for (int q = 0; q < KMAX; ++q) {
+            stage_v[((g - 1) * BM + r_local) * KMAX + q] = tv[q];
+            stage_i[((g - 1) * BM + r_local) * KMAX + q] = ti[q];
           }
         }
-        lsum += l0 + l1;
-        if (kshare) {      // publish this item's own k-th when it has risen
-          int kown = 0;
+        asm volatile("bar.sync 1, 384;" ::: "memory");
+        if (g == 0 && row_ok) {
+          float kthv = -INFINITY;
 #pragma unroll
-          for (int r = 0; r < KMAX; ++r)
-            if (r == k - 1) kown = tk[r];
-          if (kown > kpub) {
-            atomicMax(kshare, kown);
-            kpub = kown;
+          for (int q = 0; q < KMAX; ++q)
+            if (q == k - 1) kthv = tv[q];
+#pragma unroll 1
+          for (int og = 0; og < NEPI - 1; ++og) {
+            lsum += stage_l[og * BM + r_local];
+            if (outl) {
+#pragma unroll 1
+              for (int q = 0; q < k; ++q) {
+                const float x = stage_v[(og * BM + r_local) * KMAX + q];
+                if (x > kthv) {
+                  topk_insert<KMAX>(tv, ti, k, x, stage_i[(og * BM + r_local) * KMAX + q]);
+#pragma unroll
+                  for (int qq = 0; qq < KMAX; ++qq)
+                    if (qq == k - 1) kthv = tv[qq];
+                }
+              }
+            }
+          }
+          const int64_t pr = (int64_t)chunk * prm.n_rows + row;
+          sw.l_part[pr] = lsum;
+#pragma unroll
+          for (int q = 0; q < KMAX; ++q) {
+            if (q < k) {
+              sw.topv_part[pr * k + q] = tv[q];
+              sw.topi_part[pr * k + q] = ti[q];
+            }
           }
         }
-        FFC_PROF_T(e3);
-        FFC_PROF_ADD(prof_e2, e2, e3);
       }
       if (warp == 4 && lane == 0) {
         FFC_PROF_STORE(3, prof_e0);
@@ -537,71 +628,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         FFC_PROF_STORE(5, prof_e2);
         FFC_PROF_STORE(7, prof_trig);
       }
-      // ---- per-row partials: combine the three warpgroups through shared memory ----
-      float* stage_v = reinterpret_cast<float*>(sW1);                             // [2][128][KMAX] (W ring is idle now)
-      int32_t* stage_i = reinterpret_cast<int32_t*>(sW1 + 2 * BM * KMAX * 4);
-      float* stage_l = reinterpret_cast<float*>(sW1 + 4 * BM * KMAX * 4);         // [2][128]
-      // every MMA that read the W ring has completed once the last s_full was observed by its epilogue warpgroup;
-      // synchronise the 12 epilogue warps (named barrier 1) before reusing the ring as staging
-      asm volatile("bar.sync 1, 384;" ::: "memory");
-      float tv[KMAX];
-      int32_t ti[KMAX];
-#pragma unroll
-      for (int q = 0; q < KMAX; ++q) {
-        const bool live = tk[q] > 0;
-        tv[q] = live ? __int_as_float(tk[q] & (int)TOPK_VAL_MASK) : -INFINITY;
-        ti[q] = live ? tc[q] + (tk[q] & 31) : -1;
-      }
-      if (g >= 1) {
-        stage_l[(g - 1) * BM + r_local] = lsum;
-#pragma unroll
-        for (int q = 0; q < KMAX; ++q) {
-          stage_v[((g - 1) * BM + r_local) * KMAX + q] = tv[q];
-          stage_i[((g - 1) * BM + r_local) * KMAX + q] = ti[q];
-        }
-      }
-      asm volatile("bar.sync 1, 384;" ::: "memory");
-      if (g == 0 && row_ok) {
-        float kthv = -INFINITY;
-#pragma unroll
-        for (int q = 0; q < KMAX; ++q)
-          if (q == k - 1) kthv = tv[q];
-#pragma unroll 1
-        for (int og = 0; og < NEPI - 1; ++og) {
-          lsum += stage_l[og * BM + r_local];
-          if (outl) {
-#pragma unroll 1
-            for (int q = 0; q < k; ++q) {
-              const float x = stage_v[(og * BM + r_local) * KMAX + q];
-              if (x > kthv) {
-                topk_insert<KMAX>(tv, ti, k, x, stage_i[(og * BM + r_local) * KMAX + q]);
-#pragma unroll
-                for (int qq = 0; qq < KMAX; ++qq)
-                  if (qq == k - 1) kthv = tv[qq];
-              }
-            }
-          }
-        }
-        const int64_t pr = (int64_t)chunk * prm.n_rows + row;
-        sw.l_part[pr] = lsum;
-#pragma unroll
-        for (int q = 0; q < KMAX; ++q) {
-          if (q < k) {
-            sw.topv_part[pr * k + q] = tv[q];
-            sw.topi_part[pr * k + q] = ti[q];
-          }
-        }
-      }
     }
   } else {
     // =========================================== O-CTA ===========================================
     if (warp == 0) {
       // ---- TMA producer: one 3-D box (64 features x JB queue rows x D/64 feature chunks) per stage ----
-      if (n_tiles > 0 && !dbg_noO && !dbg_noTma) {
-        int stage = 0;
-        uint32_t ph = 0;
-        FFC_PROF_DECL(prof_tma);
-        for (int t = t_begin; t < t_end; ++t) {
+      int stage = 0;
+      uint32_t ph = 0;
+      FFC_PROF_DECL(prof_tma);
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        if (it.n_tiles == 0 || dbg_noO || dbg_noTma) continue;
+        const CUtensorMap* map_w2 = it.sidx == 0 ? &map_w2a : (it.sidx == 1 ? &map_w2b : &map_w2c);
+        for (int t = it.t_begin; t < it.t_begin + it.n_tiles; ++t) {
 #pragma unroll
           for (int jb = 0; jb < BN / JB; ++jb) {
             FFC_PROF_T(q0);
@@ -619,30 +658,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             }
           }
         }
-        if (lane == 0) FFC_PROF_STORE(6, prof_tma);
       }
+      if (lane == 0) FFC_PROF_STORE(6, prof_tma);
     } else if (warp == 1) {
       // ---- GEMM-2 issue: O[128 x D] += P~[128 x 128] . W_tile[128 x D]; per K = 16 queue rows one MMA per 256 features ----
-      if (n_tiles > 0) {
-        constexpr uint32_t idesc = make_idesc(BM, Sh::N2, 0, 1);
-        // A = P~: interleaved core matrices, K halves 2 KB apart (LBO), 8-row groups 128 B apart (SBO)
-        const uint64_t a0 = make_desc(smem_u32(sPt), BM * 16, 128, 0);
-        // B = W stage, MN-major (N = feature dim): 64-feature atoms JB*128 bytes apart (LBO), 8-row groups 1 KB apart (SBO)
-        const uint64_t b0 = make_desc(smem_u32(sW2), JB * 128, 1024);
-        int stage = 0, pb = 0;
-        uint32_t ph = 0, pt_ph = 0;
-        if (lane == 0) FFC_STAMP(2);
-        FFC_PROF_DECL(prof_a);
-        FFC_PROF_DECL(prof_b);
-        FFC_PROF_DECL(prof_c);
+      constexpr uint32_t idesc = make_idesc(BM, Sh::N2, 0, 1);
+      // A = P~: interleaved core matrices, K halves 2 KB apart (LBO), 8-row groups 128 B apart (SBO)
+      const uint64_t a0 = make_desc(smem_u32(sPt), BM * 16, 128, 0);
+      // B = W stage, MN-major (N = feature dim): 64-feature atoms JB*128 bytes apart (LBO), 8-row groups 1 KB apart (SBO)
+      const uint64_t b0 = make_desc(smem_u32(sW2), JB * 128, 1024);
+      int stage = 0, pb = 0;
+      uint32_t ph = 0, pt_ph = 0;
+      uint32_t ni = 0;      // items with tiles so far
+      FFC_PROF_DECL(prof_a);
+      FFC_PROF_DECL(prof_b);
+      FFC_PROF_DECL(prof_c);
+      FFC_PROF_DECL(prof_gap);
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        const int n_tiles = it.n_tiles;
+        if (n_tiles == 0) continue;
+        if (ni > 0) {     // the previous item's O has been read out of TMEM by the write-out warps
+          FFC_PROF_T(g0);
+          mbar_wait(&bars.o_empty, (ni - 1) & 1);
+          FFC_PROF_T(g1);
+          FFC_PROF_ADD(prof_gap, g0, g1);
+        }
+        tc_fence_after();
+        if (ni == 0 && lane == 0) FFC_STAMP(2);
         for (int i = 0; i < n_tiles; ++i) {
           FFC_PROF_T(q0);
           if (!dbg_noHand) mbar_wait(&bars.pt_ready[pb], pt_ph);     // P~ complete and fenced by the hand-off warp
           tc_fence_after();
           FFC_PROF_T(q1);
           FFC_PROF_ADD(prof_a, q0, q1);
+          // the P~ buffer of the item's LAST tile is not released here: the write-out warps stage O through it and release it
+          const bool release_pt = i + 1 < n_tiles && !dbg_noHand;
           if (dbg_noO) {
-            if (!dbg_noHand && elect_one()) mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb]), 0));
+            if (release_pt && elect_one()) mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb]), 0));
             __syncwarp();
           } else {
             const uint64_t ap = a0 + (uint64_t)(pb * (PT_BYTES >> 4));
@@ -669,7 +722,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                 }
                 if (!dbg_noTma) tc_commit(&bars.w2_empty[stage]);
                 // frees P~ buffer pb: arrives in the S-CTA (cluster rank 0)
-                if (jb == BN / JB - 1 && !dbg_noHand) tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);
+                if (jb == BN / JB - 1 && release_pt) tc_commit_mcast(&bars.pt_empty[pb], (uint16_t)1);
               }
               __syncwarp();
               FFC_PROF_T(q4);
@@ -689,24 +742,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           if (dbg_noO) mbar_arrive(&bars.o_full); else tc_commit(&bars.o_full);
         }
         __syncwarp();
-        if (lane == 0) {
-          FFC_STAMP(3);
-          FFC_PROF_STORE(0, prof_a);
-          FFC_PROF_STORE(1, prof_b);
-          FFC_PROF_STORE(2, prof_c);
-        }
-        mbar_wait(&bars.o_full, 0);     // one polling warp; the 8 epilogue warps block on a hardware barrier instead
+        if (lane == 0) FFC_STAMP(3);
+        mbar_wait(&bars.o_full, ni & 1);     // one polling warp; the 8 write-out warps block on a hardware barrier instead
+        __syncwarp();
+        asm volatile("bar.sync 2, 288;" ::: "memory");
+        ++ni;
       }
-      __syncwarp();
-      asm volatile("bar.sync 2, 288;" ::: "memory");
+      if (lane == 0) {
+        FFC_PROF_STORE(0, prof_a);
+        FFC_PROF_STORE(1, prof_b);
+        FFC_PROF_STORE(2, prof_c);
+        FFC_PROF_STORE(7, prof_gap);
+      }
     } else if (warp == 3) {
       // ---- P~ hand-off: wait for the peer's 32 KB (st.async complete_tx bytes), make the generic-proxy writes visible to the
       // async proxy (tcgen05.mma reads P~ through it) and pass the buffer on.  The fence costs 200-1100 cycles while TMA
       // loads are in flight, so it lives here and not in the MMA warp.
-      if (n_tiles > 0 && !dbg_noHand) {
-        int pb = 0;
-        uint32_t pt_ph = 0;
-        for (int i = 0; i < n_tiles; ++i) {
+      int pb = 0;
+      uint32_t pt_ph = 0;
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        if (dbg_noHand) break;
+        for (int i = 0; i < it.n_tiles; ++i) {
           if (elect_one()) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);     // the single arriver of pt_full[pb]
           __syncwarp();
           mbar_wait_cluster(&bars.pt_full[pb], pt_ph);
@@ -721,54 +778,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         }
       }
     } else if (warp >= 4 && warp < 12) {
-      // ---- O epilogue: TMEM -> global partial [chunk][row][D]; warpgroup g takes half of the columns ----
+      // ---- O write-out: TMEM -> global partial [chunk][row][D]; warpgroup g takes half of the columns ----
       const int g = (warp - 4) >> 2;
       const int q4 = warp & 3;
-      const int r_local = q4 * 32 + lane;
-      const int row = row0 + r_local;
-      const bool row_ok = row < prm.n_rows;
-      asm volatile("bar.sync 2, 288;" ::: "memory");   // released by the MMA warp once every tcgen05.mma of the item has completed
-      tc_fence_after();
       constexpr int half = D / 2;                  // D is a multiple of 64
-      // A TMEM lane is a row, so a thread holds 32 consecutive floats of ITS row: stored straight from the registers every store
-      // instruction touched 32 different 2 KB-strided rows, 16 bytes each (the write-out took 12-17 us per item, the CTA pair's
-      // largest fixed cost).  Each warp transposes its 32 x 32 block through 4.5 KB of the idle P~ buffers instead: a store
-      // instruction then covers 4 rows x 128 contiguous bytes.
-      float* stg = reinterpret_cast<float*>(sPt) + (warp - 4) * (32 * 36);
-      float* dst0 = sw.o_part + ((int64_t)chunk * prm.n_rows + row0 + q4 * 32) * D + g * half;
-      (void)row_ok;
-      for (int c0 = 0; c0 < half; c0 += 32) {
-        uint32_t v[32];
-        if (n_tiles > 0) {
+      uint32_t gtiles = 0;      // the CTA's tile count at the start of the current item
+      for (int ia = pair; ia < n_items; ia += n_pairs) {
+        const Item it = decode_item(prm, ia);
+        const SubSweep& sw = prm.sub[it.sidx];
+        const int row0 = it.row0, n_tiles = it.n_tiles;
+        float* dst0 = sw.o_part + ((int64_t)it.chunk * prm.n_rows + row0 + q4 * 32) * D + g * half;
+        if (n_tiles == 0) {
+          // an item without columns owes a zero partial (4 rows x 128 B per store instruction)
+          for (int c0 = 0; c0 < half; c0 += 32) {
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int r = itr * 4 + (lane >> 3), c = (lane & 7) * 4;
+              if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c) = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          continue;
+        }
+        asm volatile("bar.sync 2, 288;" ::: "memory");   // released by the MMA warp once every tcgen05.mma of the item has completed
+        tc_fence_after();
+        // A TMEM lane is a row, so a thread holds 32 consecutive floats of ITS row: stored straight from the registers every store
+        // instruction touched 32 different 2 KB-strided rows, 16 bytes each (the write-out took 12-17 us per item).  Each warp
+        // transposes its 32 x 32 block through 4 KB of shared memory instead -- 16-byte pieces XOR-swizzled by the row, so both the
+        // row-wise writes and the reads are conflict-free -- and a store instruction then covers 4 rows x 128 contiguous bytes.
+        // The 8 x 4 KB are the P~ buffer of the item's last tile: its MMAs have completed, and the S-CTA may not refill it until the
+        // write-out warps release it below (its two other buffers are already being filled for the next item).
+        const int pb_last = (int)((gtiles + (uint32_t)n_tiles - 1u) % NPB);
+        unsigned char* stg = sPt + pb_last * PT_BYTES + (warp - 4) * 4096;
+        for (int c0 = 0; c0 < half; c0 += 32) {
+          uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(g * half + c0), v);
-        } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = 0u;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int r = itr * 4 + (lane >> 3), c = lane & 7;
+            const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+            if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c * 4) = x;
+          }
+          __syncwarp();
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3), c = (lane & 7) * 4;
-          const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 36 + c);
-          if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c) = x;
+        tc_fence_before();
+        asm volatile("bar.sync 3, 256;" ::: "memory");      // the 8 write-out warps: O is out of TMEM, the staging buffer is idle
+        if (warp == 4) {
+          if (elect_one()) {
+            mbar_arrive(&bars.o_empty);
+            if (!dbg_noHand) mbar_arrive_remote(map_to_rank(smem_u32(&bars.pt_empty[pb_last]), 0));
+          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      tc_fence_before();
-    }
-  }
-  // S-CTA with no tiles still owes l / top-k partials (zeros / -inf): handled here for uniformity
-  if (rank == 0 && n_tiles == 0 && warp >= 4 && warp < 8) {
-    const int r_local = (warp & 3) * 32 + lane;
-    const int row = row0 + r_local;
-    if (row < prm.n_rows) {
-      const int64_t pr = (int64_t)chunk * prm.n_rows + row;
-      sw.l_part[pr] = 0.f;
-      for (int q = 0; q < prm.k; ++q) {
-        sw.topv_part[pr * prm.k + q] = -INFINITY;
-        sw.topi_part[pr * prm.k + q] = -1;
+        gtiles += (uint32_t)n_tiles;
       }
     }
   }
@@ -855,23 +920,60 @@ static bool use_one_cta(int D) {
   return D <= 256 && !force_pair;
 }
 
-int sm100_pick_chunks(int n_rows, int64_t n_cols, int D) {
+// CTA pairs that can be resident at once (one CTA per SM, both CTAs of a pair on one TPC): the persistent grid
+static int pair_slots() {
+  static int slots = 0;
+  if (!slots) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms >= 2) slots = sms / 2;
+    else slots = 74;
+    const char* e = getenv("FFC_SWEEP_PAIRS");
+    if (e && atoi(e) > 0) slots = atoi(e);
+  }
+  return slots;
+}
+// Launch shape of the CTA-pair kernel.  Default: one pair per item, dealt to the SMs by the hardware (the kernel's item loop runs once).
+// FFC_SWEEP_PERSISTENT=1 (or a pair count forced with FFC_SWEEP_PAIRS): with more than 2 x slots items the grid is `slots` persistent
+// pairs that walk the item list, so that set-up, P load and O write-out of consecutive items overlap.  Measured at the 2 / 4 / 8-way
+// shard shapes (profiles/r2_persistent_sweep.md) it is no faster: the steady state is bound by L2 -> SM delivery of W (13.4 TB/s,
+// both CTAs of every pair stream every tile), the turn-around it removes was overlapped with other pairs' tiles anyway, and the
+// hardware's dynamic dealing balances the short side items better than a static round-robin.  Kept as a tested option.
+static bool persistent_grid(int n_items) {
+  static const bool on = (getenv("FFC_SWEEP_PERSISTENT") != nullptr && atoi(getenv("FFC_SWEEP_PERSISTENT")) != 0) ||
+                         (getenv("FFC_SWEEP_PAIRS") != nullptr && atoi(getenv("FFC_SWEEP_PAIRS")) > 0);
+  return on && n_items > 2 * pair_slots();
+}
+// Pairs of the persistent grid.  FFC_SWEEP_RESERVE (pairs, default 0) leaves TPCs to the kernels that run underneath a sweep on other
+// streams (LRU / label bookkeeping, the label prefetch's collectives): a grid that never gives an SM back pushes them behind the whole sweep.
+static int persistent_pairs() {
+  static const int reserve = getenv("FFC_SWEEP_RESERVE") ? atoi(getenv("FFC_SWEEP_RESERVE")) : 0;
+  const int slots = pair_slots();
+  return slots > 8 ? std::max(8, slots - std::max(0, reserve)) : slots;
+}
+
+int sm100_pick_chunks(int n_rows, int64_t n_cols, int D, int chunk_cap) {
   // items = row_tiles x chunks run as CTA pairs, 74 pairs at a time (one-CTA kernel: 148 CTAs): pick the chunk count whose last
   // wave is fullest (ties -> fewer chunks: fewer partials and fewer P loads / O write-outs)
   const bool one = use_one_cta(D);
-  const int slots = one ? 148 : 74;
+  const int slots = one ? 148 : pair_slots();
+  static const int forced = getenv("FFC_SWEEP_CHUNKS") ? atoi(getenv("FFC_SWEEP_CHUNKS")) : 0;     // tests: a fixed chunk count
+  if (forced > 0) return (int)std::min<int64_t>(std::min(forced, std::max(1, chunk_cap)), std::max<int64_t>(1, ceil_div64(n_cols, one ? sm100_1cta_tile_cols(D) : BN)));
   const int tile_cols = one ? sm100_1cta_tile_cols(D) : BN;
   const int row_tiles = std::max(1, (n_rows + BM - 1) / BM);
   const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(n_cols, tile_cols));
-  const int max_c = (int)std::min<int64_t>(n_tiles, 40);
+  const int max_c = (int)std::min<int64_t>(n_tiles, std::max(1, std::min(chunk_cap, 40)));      // chunk_cap: what the caller's partial workspace holds
   int best = 1;
   double best_eff = 0.0;
   for (int c = 1; c <= max_c; ++c) {
     const int items = row_tiles * c;
-    const int waves = (items + slots - 1) / slots;
-    // every item pays a fixed cost (prologue, P load, O write-out) worth about 12 tile-times (of 128 columns)
+    const bool pers = !one && persistent_grid(items);
+    const int slots_c = pers ? persistent_pairs() : slots;
+    const int waves = (items + slots_c - 1) / slots_c;
+    // every item pays a fixed cost (P load, O write-out and the partial's trip through HBM; one pair per item: also set-up and the
+    // cluster launch) worth about 12 tile-times (of 128 columns), about 7 on the persistent grid where consecutive items overlap
+    const double fixed = pers ? 7.0 : 12.0;
     const double tiles_per_item = (double)n_tiles / c * tile_cols / 128.0;
-    const double eff = ((double)items / (waves * (double)slots)) * (tiles_per_item / (tiles_per_item + 12.0));
+    const double eff = ((double)items / (waves * (double)slots_c)) * (tiles_per_item / (tiles_per_item + fixed));
     if (eff > best_eff * 1.005) {
       best_eff = eff;
       best = c;
@@ -889,7 +991,8 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
     FFC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  kern<<<dim3(2 * n_items), dim3(NTHREADS), smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
+  const int n_pairs = persistent_grid(n_items) ? persistent_pairs() : n_items;
+  kern<<<dim3(2 * n_pairs), dim3(NTHREADS), smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], p);
   FFC_LAUNCH_CHECK();
 #if FFC_SM100_DEBUG_BUILD
   static int dumps_left = getenv("FFC_SM100_DUMP") ? atoi(getenv("FFC_SM100_DUMP")) : 0;
@@ -900,13 +1003,16 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
     if (!fo) fo = stderr;
     static long long h[1024][8];
     cudaMemcpyFromSymbol(h, g_sweep_stamps, sizeof(h));
-    const int n = std::min(2 * std::min(n_items, p.sub[1].item0), 1024);     // main-sweep CTAs only
+    const bool pers = n_pairs < n_items;
+    const int main_items = std::min(n_items, p.sub[1].item0);
+    const int n = std::min(2 * (pers ? n_pairs : main_items), 1024);     // one pair per item: main-sweep CTAs only
     long long t0 = h[0][6], t1 = 0;
     for (int i = 0; i < n; ++i) {
       t0 = std::min(t0, h[i][6]);
       t1 = std::max(t1, h[i][7]);
     }
-    fprintf(fo, "[sweep stamps] debug=%d %d CTAs, kernel %.1f us (globaltimer)\n", p.debug, 2 * n_items, (t1 - t0) * 1e-3);
+    fprintf(fo, "[sweep stamps] debug=%d %d items on %d CTAs%s, kernel %.1f us (globaltimer)\n", p.debug, n_items, 2 * n_pairs, pers ? " (persistent pairs)" : "",
+            (t1 - t0) * 1e-3);
     // where an item's time goes (cycles, mean over the CTAs of each role): set-up (barriers, TMEM alloc, cluster sync) | until the
     // MMA loop starts (P into TMEM / first W tile) | MMA loop | after the loop to the end of the role's work (O write-out, partial
     // merge) | final cluster sync + dealloc
@@ -930,12 +1036,14 @@ static int launch_one(const CUtensorMap* maps, const Sm100Params& p, int n_items
       int cnt = 0;
       for (int i = role; i < n; i += 2, ++cnt)
         for (int k = 0; k < 8; ++k) acc[k] += (double)hp[i][k];
-      const double nt = (double)p.sub[0].tiles_per_chunk;
+      // tiles per CTA (persistent pairs: the main sweep's tiles spread over the pairs; the side items' few tiles are not counted)
+      const double nt = pers ? (double)p.sub[0].tiles_per_chunk * main_items / n_pairs : (double)p.sub[0].tiles_per_chunk;
       fprintf(fo, "  %s-CTA cycles/tile: MMA warp waits for %s %.0f, waits for W %.0f, issues %.0f | TMA producer waits %.0f", role ? "O" : "S",
               role ? "P~" : "a free S buffer", acc[0] / cnt / nt, acc[1] / cnt / nt, acc[2] / cnt / nt, acc[6] / cnt / nt);
       if (role == 0)
         fprintf(fo, " | epilogue warp (1 of 3 warpgroups; per tile of the CTA): waits for S %.0f, waits for a free P~ buffer %.0f, works %.0f; top-k scans in %.1f%% of its 32-column chunks", acc[3] / cnt / nt,
                 acc[4] / cnt / nt, acc[5] / cnt / nt, 100.0 * acc[7] / cnt / (nt / 3.0 * 4.0));
+      if (role == 1) fprintf(fo, " | MMA warp idle between items (O read-out) %.0f per CTA", acc[7] / cnt);
       fprintf(fo, "\n");
     }
     if (fo != stderr) fclose(fo);
@@ -1000,6 +1108,7 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
     sb.topi_part = w.topi_part;
     n_items += row_tiles * w.n_chunks;
   }
+  p.n_items = n_items;
 #define FFC_SWEEP_CASE(DV)                                                       \
   case DV:                                                                       \
     return a.sv ? launch_one<true, DV>(maps, p, n_items, s) : launch_one<false, DV>(maps, p, n_items, s);

@@ -257,6 +257,7 @@ struct SubSweep {
 };
 struct Sm100Params {
   int n_rows;
+  int n_items;                // work items of the launch (all sub-sweeps); the CTA-pair kernel's persistent pairs walk this list
   const __nv_bfloat16* p16;   // [n_rows, D] probe rows (bf16), loaded straight into TMEM when P_TMEM
   const uint8_t* is_out;
   int32_t* kth_shared;        // [n_rows] shared hard-negative threshold (integer key), zeroed by the prep kernel

@@ -129,3 +129,10 @@ def ptr(t):
 def stream_ptr(device=None):
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def side_stream_priority():
+    """Priority of the bookkeeping streams (LRU / label kernels that run underneath the sweeps): -1 = above the caller's stream, so
+    that their pending blocks are placed before the sweep's pending CTAs whenever an SM frees up.  FFC_SIDE_PRIORITY overrides (0 =
+    default priority: the behaviour before this switch existed; for A/B timing)."""
+    return int(os.environ.get('FFC_SIDE_PRIORITY', '-1'))

@@ -292,7 +292,9 @@ class ShardedFFCHead:
         self._nccl = dist.get_backend(group) == 'nccl'
         self._stats = {}
         self._timing = [] if (os.environ.get('FFC_DIST_TIMING') and self._nccl) else None
-        self._side = torch.cuda.Stream(device=self.dev) if (self._nccl and not os.environ.get('FFC_DIST_NO_OVERLAP')) else None
+        # bookkeeping stream, high priority: its short kernels get the SMs a sweep CTA frees before the sweep's own pending CTAs do
+        self._side = (torch.cuda.Stream(device=self.dev, priority=_capi.side_stream_priority())
+                      if (self._nccl and not os.environ.get('FFC_DIST_NO_OVERLAP')) else None)
         self._pre = None            # labels + rollback-pass bookkeeping of the next forward_pair (see prefetch)
         self.prefetch_hits = 0      # forward_pair calls that consumed prefetched bookkeeping
         # prefetch's collectives get their own communicator: torch's NCCL backend runs all collectives of one process group on one

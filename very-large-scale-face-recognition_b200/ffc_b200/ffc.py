@@ -146,7 +146,9 @@ class FFCHead(Module):
             self.queue_bf16 = torch.empty(2, Q, D, dtype=torch.bfloat16, device=dev)
             self._alloc_batch(R)
             # LRU bookkeeping runs on its own stream, ahead of the sweeps of the main stream (see forward_pair)
-            self._side = torch.cuda.Stream(device=dev)
+            # (high priority: its short kernels take the SMs a sweep CTA frees before the sweep's next CTAs do, instead of queueing
+            # behind the whole sweep grid)
+            self._side = torch.cuda.Stream(device=dev, priority=_capi.side_stream_priority())
             self._lru_sync_main = True
             cfg = HeadConfig(R, Q, Q, 0, D, _capi.LOSS_TYPES[self.loss_type], self.scale, self.margin, self.hard_neg,
                              _capi.PRECISIONS[self.precision])
