@@ -327,6 +327,19 @@ def kernel_micro(head, w, dev, world):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def softmax_rows(head, rows):
+    """Rows of the last pass that have a softmax term (label known), rounded up to whole 128-row tiles: the rows GEMM-2 runs for."""
+    lab = None
+    if getattr(head, '_last', None) is not None:                      # ShardedFFCHead: the commit pass's all-reduced labels
+        lab = head._last['label']
+    elif getattr(head, '_sets', None) is not None:                    # FFCHead: bookkeeping set 1 = the commit pass
+        lab = head._sets[1]['label']
+    if lab is None:
+        return rows
+    n_soft = int((lab[:rows] >= 0).sum().item())
+    return min(rows, (n_soft + 127) // 128 * 128)
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -466,7 +479,12 @@ def run_ours(args, w):
     pk = peaks()
     rows_per_sweep = B * world
     q_local = Q // world
-    flops = 4.0 * rows_per_sweep * q_local * D                     # algorithmic FLOPs of one main sweep launch (4*B*Q*D)
+    # Algorithmic FLOPs of one main sweep launch: 2*rows*Q*D for the cosines of every row + 2*rows'*Q*D for the gradient sum of the rows
+    # that have a softmax term (a row whose label is unknown -- ffc.py:61, label -1 -- only takes part in the hard-negative top-k of its
+    # cosines: no p~, no second GEMM; the kernel sweeps such rows last and skips GEMM-2 for row tiles made of them).  rows' is counted
+    # in whole 128-row tiles from the labels of the last timed pass; C3 (every label known) has rows' = rows, i.e. 4*B*Q*D.
+    soft_rows = softmax_rows(head, rows_per_sweep)
+    flops = 2.0 * (rows_per_sweep + soft_rows) * q_local * D
     ach = flops * sweep_n / (sweep_ms * 1e-3) / 1e12 if sweep_ms > 0 else 0.0
     # the burst figure for a kernel timed in a short region, the sustained one when the timed region is long enough for the board to
     # settle at its power cap (MEASURED_PEAKS.json: best of 10 vs back to back for 4 s)
@@ -484,7 +502,7 @@ def run_ours(args, w):
                     gpu_launches=int(launches),
                     roofline=dict(bound='tensor', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak, traffic=sweep_traffic(w, world),
                                   kernel='ffc_head_sweep_sm100_kernel (main sweep)', launches=int(sweep_n), avg_ms=sweep_ms / max(1, sweep_n),
-                                  algorithmic_flops_per_launch=flops,
+                                  algorithmic_flops_per_launch=flops, rows_per_launch=rows_per_sweep, rows_with_softmax_term=soft_rows,
                                   peak_kind=('bf16_tflops_sustained' if long_run else 'bf16_tflops (burst)') + f' ({pk["src"]}; timed region {ms / 1e3:.2f} s)',
                                   frac_of_burst=ach / pk['burst'], frac_of_sustained=ach / pk['sustained'], sweep_share_of_step=sweep_ms / ms),
                     clocks=clk, loss=loss_val)

@@ -33,6 +33,8 @@ struct ffc_head {
   int32_t* kth_shared;         // [max_rows] hard-negative threshold shared by the column chunks of the tcgen05 sweep
   float* thr;                  // [2][max_rows]
   int32_t* counts;             // [2][2] n_pos, n_out, double-buffered by pass parity
+  int32_t* row_map;            // [max_rows] sweep position -> probe row: positives first, hard-negative-only rows last (prep kernel's last block)
+  int32_t* part_ctr;           // [2]: arrival counter of the prep blocks, number of rows in front of the hard-negative-only rows
   int pass_parity;
   int prepared_rows;           // rows of the last ffc_head_prep not yet swept (ffc_head_prep / ffc_head_sweep_prepared pairing), else <= 0
   ffc::ReduceJobs* jobs;        // partial-result descriptors of the last merged sweep launch (one-GPU fast path)
@@ -179,7 +181,8 @@ __global__ void __launch_bounds__(128) head_prep_fused_kernel(const float* __res
                                                               float* __restrict__ side_f32, __nv_bfloat16* __restrict__ side_bf16,
                                                               int32_t* __restrict__ tcol, int32_t* __restrict__ tpos, uint8_t* __restrict__ is_out,
                                                               int32_t* __restrict__ kth_shared, int32_t* counts_cur, int32_t* counts_next, float margin,
-                                                              float* __restrict__ tgt, float* __restrict__ thr) {
+                                                              float* __restrict__ tgt, float* __restrict__ thr, int32_t* __restrict__ row_map,
+                                                              int32_t* part_ctr) {
   const int b = blockIdx.x;
   const int no = *n_ones_p;
   __shared__ int found;
@@ -260,6 +263,41 @@ __global__ void __launch_bounds__(128) head_prep_fused_kernel(const float* __res
       for (int d = threadIdx.x; d < D; d += blockDim.x) {
         if (side_f32) side_f32[dst + d] = live ? qf[src + d] : 0.f;
         if (side_bf16) side_bf16[dst + d] = live ? qh[src + d] : __float2bfloat16(0.f);
+      }
+    }
+  }
+  // Row order of the tcgen05 sweep: the last block to arrive writes the stable partition "rows with a softmax term first, hard-negative-
+  // only rows (label -1, ffc.py:61) last" -- row tiles made of the latter need neither exponentials nor the second GEMM -- and the
+  // number of rows in front.  At the very-large-scale end (C4: ten identities per queue slot) nine rows in ten are of that kind.
+  if (row_map) {
+    __shared__ int s_last;
+    __shared__ int s_cnt[128];
+    __threadfence();                    // this block's is_out[] is visible before its arrival is
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(part_ctr, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const volatile uint8_t* vo = is_out;
+      const int per = (n_rows + 127) / 128, r_begin = min(n_rows, (int)threadIdx.x * per), r_end = min(n_rows, r_begin + per);
+      int np = 0;
+      for (int i = r_begin; i < r_end; ++i) np += vo[i] ? 0 : 1;
+      s_cnt[threadIdx.x] = np;
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int t = 0; t < 128; ++t) {
+        const int c = s_cnt[t];
+        if (t < (int)threadIdx.x) before += c;
+        total += c;
+      }
+      int wp = before, wo = total + (r_begin - before);      // next free position among the positives / the hard-negative-only rows
+      for (int i = r_begin; i < r_end; ++i) {
+        if (vo[i]) row_map[wo++] = i;
+        else row_map[wp++] = i;
+      }
+      if (threadIdx.x == 0) {
+        part_ctr[1] = total;
+        part_ctr[0] = 0;
       }
     }
   }
@@ -488,9 +526,10 @@ __global__ void __launch_bounds__(128) head_reduce_multi_kernel(const ReduceJobs
   const ReduceJob& r = jobs.j[blockIdx.y];
   const int i = blockIdx.x;
   const int n_chunks = r.n_chunks;
+  const bool no_o = is_out[i] != 0;      // a hard-negative-only row has no softmax term: its O partials may not even have been written
   for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c = 0; c < n_chunks && !no_o; ++c) {
       const float4 v = *reinterpret_cast<const float4*>(r.o_part + ((int64_t)c * n_rows + i) * D + d);
       acc.x += v.x;
       acc.y += v.y;
@@ -638,7 +677,8 @@ __device__ __forceinline__ void row_coef_math(const FinalizeArgs& a, int i, int 
             int32_t idx;
             top_at(r, set, q, v, idx);
             // a side entry is tagged in bit 30: under loss 2 it reads queue[1]
-            if (v > tv[k - 1]) topk_insert<KMAX>(tv, ti, k, v, (int32_t)(idx | (src ? 0x40000000 : 0)));
+            if (!(v > tv[k - 1])) break;      // every candidate list is sorted: nothing further of this one can enter
+            topk_insert<KMAX>(tv, ti, k, v, (int32_t)(idx | (src ? 0x40000000 : 0)));
           }
         }
       for (int q = 0; q < k; ++q) {
@@ -1106,6 +1146,9 @@ extern "C" int ffc_head_create(const ffc_head_config* cfg, ffc_head_t** out) {
   FFC_CUDA(cudaMalloc(&h->thr, 2 * R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->counts, 4 * sizeof(int32_t)));
   FFC_CUDA(cudaMemset(h->counts, 0, 4 * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->row_map, R * sizeof(int32_t)));
+  FFC_CUDA(cudaMalloc(&h->part_ctr, 2 * sizeof(int32_t)));
+  FFC_CUDA(cudaMemset(h->part_ctr, 0, 2 * sizeof(int32_t)));
   FFC_CUDA(cudaMalloc(&h->row_loss, R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->coef, 4 * R * sizeof(float)));
   FFC_CUDA(cudaMalloc(&h->nslot, R * sizeof(int32_t)));
@@ -1130,6 +1173,8 @@ extern "C" int ffc_head_destroy(ffc_head_t* h) {
   cudaFree(h->tcol);
   cudaFree(h->tpos);
   cudaFree(h->is_out);
+  cudaFree(h->row_map);
+  cudaFree(h->part_ctr);
   cudaFree(h->kth_shared);
   cudaFree(h->pc16);
   cudaFree(h->dq_l);
@@ -1276,6 +1321,13 @@ __global__ void __launch_bounds__(128) head_thr_from_tgt_kernel(const float* __r
   thr[n + i] = has ? tgt[n + i] - margin : INFINITY;
 }
 
+// The merged bf16 AM / Arc sweep (CTA-pair kernel) takes its rows in "hard-negative-only rows last" order; FFC_SWEEP_NO_ROWMAP=1 keeps the
+// identity order (A/B measurements).  SV sweeps and the check mode do not use it.
+static bool use_row_map(const ffc_head* h) {
+  static const bool off = getenv("FFC_SWEEP_NO_ROWMAP") != nullptr && atoi(getenv("FFC_SWEEP_NO_ROWMAP")) != 0;
+  return !off && h->cfg.precision == FFC_PREC_BF16 && h->cfg.loss_type != FFC_LOSS_SV;
+}
+
 // phase: 1 = prep only, 2 = sweeps only (prep was run by ffc_head_prep; SV thresholds are re-derived from out->tgt), 3 = both
 static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_stats* out, bool defer_reduce, void* stream, int phase = 3) {
   FFC_REQUIRE(h && in && out, "ffc_head_sweep: NULL argument");
@@ -1301,11 +1353,11 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
     if (bf16)
       head_prep_fused_kernel<true><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
                                                         in->n_ones, c.max_rows, nullptr, h->side_bf16, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
-                                                        out->tgt, sv ? h->thr : nullptr);
+                                                        out->tgt, sv ? h->thr : nullptr, use_row_map(h) ? h->row_map : nullptr, h->part_ctr);
     else
       head_prep_fused_kernel<false><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
                                                          in->n_ones, c.max_rows, h->side_f32, nullptr, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
-                                                         out->tgt, sv ? h->thr : nullptr);
+                                                         out->tgt, sv ? h->thr : nullptr, nullptr, h->part_ctr);
     FFC_LAUNCH_CHECK();
     h->prepared_rows = n;
   }
@@ -1327,6 +1379,10 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
   a.D = D;
   a.is_out = h->is_out;
   a.kth_shared = h->kth_shared;
+  if (use_row_map(h)) {      // (written by this pass's prep launch)
+    a.row_map = h->row_map;
+    a.n_pos_dev = h->part_ctr + 1;
+  }
   a.scale = c.scale;
   a.fixed_max = fixed_max_of(c);
   a.sv = sv;

@@ -142,6 +142,7 @@ struct SweepShape {
 struct Item {
   int sidx, chunk, row0, t_begin, n_tiles;
   int64_t n_cols;
+  bool all_out;      // every probe row of the item is a hard-negative-only row (see Sm100Params::row_map): no softmax term, no GEMM-2
 };
 __device__ __forceinline__ Item decode_item(const Sm100Params& prm, int item_all) {
   Item it;
@@ -157,6 +158,7 @@ __device__ __forceinline__ Item decode_item(const Sm100Params& prm, int item_all
   int t_end = it.t_begin + sw.tiles_per_chunk;
   if (t_end > n_tiles_total) t_end = n_tiles_total;
   it.n_tiles = t_end > it.t_begin ? t_end - it.t_begin : 0;
+  it.all_out = prm.n_pos_dev != nullptr && it.row0 >= *prm.n_pos_dev;
   return it;
 }
 
@@ -340,11 +342,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       int32_t* stage_i = reinterpret_cast<int32_t*>(item_stage + (NEPI - 1) * BM * 4 * (1 + KMAX));    // [2][128][KMAX]
       const uint32_t pt_remote0 = map_to_rank(smem_u32(smem + OFF_DATA), 1);
       const uint32_t ptfull_remote0 = map_to_rank(smem_u32(&bars.pt_full[0]), 1);
-      // tile gi uses S buffer gi % NSB and P~ buffer gi % NPB; NEPI == NPB, so this warpgroup always writes P~ buffer g
-      static_assert(NEPI == NPB, "epilogue warpgroups and P~ buffers are paired");
-      const int pb = g;
-      uint32_t pt_use = 0;      // tiles this warpgroup has taken so far (all items): phase of s_full[g] / pt_empty[g]
+      uint32_t s_use = 0;       // tiles this warpgroup has taken so far (all items): phase of s_full[g]
       uint32_t gi0 = 0;         // the CTA's tile count at the start of the current item
+      uint32_t hi0 = 0;         // ... counting only tiles handed to the O-CTA (not those of hard-negative-only items): tile h uses P~ buffer h % NPB
       FFC_PROF_DECL(prof_e0);
       FFC_PROF_DECL(prof_e1);
       FFC_PROF_DECL(prof_e2);
@@ -354,8 +354,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const SubSweep& sw = prm.sub[it.sidx];
         const int sidx = it.sidx, chunk = it.chunk, row0 = it.row0, t_begin = it.t_begin, n_tiles = it.n_tiles;
         const int64_t n_cols = it.n_cols;
-        const int row = row0 + r_local;
-        const bool row_ok = row < prm.n_rows;
+        // sweep position -> probe row: with a row map the rows are swept in "positives first, hard-negative-only rows last" order
+        const int pos = row0 + r_local;
+        const bool row_ok = pos < prm.n_rows;
+        const int row = row_ok ? (prm.row_map ? prm.row_map[pos] : pos) : 0;
+        const bool all_out = it.all_out;
         if (n_tiles == 0) {
           // an item without columns still owes its l / top-k partials (zeros / -inf)
           if (g == 0 && row_ok) {
@@ -413,8 +416,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.p_full);
         }
+        if (sidx == 0 && warp_out && prm.done_flags) {
+          // Seed the row's list with the hard negatives that FINISHED items of the same probe rows (other column chunks, earlier waves
+          // of the grid) have already found: entries with column -2, dropped again when the item's own partial is written.  The
+          // list's k-th is then the exact k-th over all finished columns plus this item's, instead of starting from zero -- without
+          // it an item only learns from its own columns, and at the 8-way shard shape 70 % of the 32-column chunks of an outlier-heavy
+          // batch ran the exact scan (27 % with the seeds; profiles/r2_outlier_sweep.md).  Runs while the first GEMM-1 is in flight.
+          const int n_row_tiles = (prm.n_rows + BM - 1) / BM;
+          const int32_t* flag = prm.done_flags + row0 / BM;
+          for (int c2 = 0; c2 < sw.n_chunks; ++c2) {
+            if (c2 == chunk) continue;
+            int f;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(flag + (int64_t)c2 * n_row_tiles) : "memory");
+            if (f != prm.epoch || !outl) continue;
+            const float* pv = sw.topv_part + ((int64_t)c2 * prm.n_rows + row) * k;
+            float xs[KMAX];
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) xs[q] = q < k ? __ldcg(pv + q) : -INFINITY;      // independent loads, one round trip
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) {
+              const int xk = (int)(__float_as_uint(xs[q]) & TOPK_VAL_MASK);
+              if (xs[q] > 0.f && xk > kth) {      // (sorted: once one fails the rest does too)
+                topk_insert_key(xk, -2, k, tk, tc);
+#pragma unroll
+                for (int r = 0; r < KMAX; ++r)
+                  if (r == k - 1) kth = tk[r];
+              }
+            }
+          }
+          if (outl) {
+            if (kth > 0) {
+              atomicMax(kshare, kth);
+              kpub = kth;
+            }
+          }
+        }
         const int first = (g + NEPI - (int)(gi0 % NEPI)) % NEPI;      // this warpgroup's first tile of the item
-        for (int i = first; i < n_tiles; i += NEPI, ++pt_use) {
+        for (int i = first; i < n_tiles; i += NEPI, ++s_use) {
           const int sb = (int)((gi0 + (uint32_t)i) & (NSB - 1));
           const int j0 = (t_begin + i) * BN;
           // exclusion words of the four 32-column chunks of this tile (one 16-byte load, issued before the waits)
@@ -423,13 +461,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           int kshared = 0;
           if (kshare) kshared = __ldcg(kshare);
           FFC_PROF_T(e0);
-          // s_full is per warpgroup: this is the warpgroup's pt_use-th tile.  (Per-buffer barriers would be waited by
+          // s_full is per warpgroup: this is the warpgroup's s_use-th tile.  (Per-buffer barriers would be waited by
           // different warpgroups in turn; with fewer S buffers than warpgroups + 1 a slow warpgroup gets lapped by a phase and
           // a parity wait two phases behind never returns.)
-          mbar_wait(&bars.s_full[g], pt_use & 1);
+          mbar_wait(&bars.s_full[g], s_use & 1);
           tc_fence_after();
           FFC_PROF_T(e1);
-          if (!dbg_noHand) mbar_wait_cluster(&bars.pt_empty[pb], (pt_use & 1) ^ 1);
+          const uint32_t hi = hi0 + (uint32_t)i;          // the tile's number among the tiles handed to the O-CTA
+          const int pb = (int)(hi % NPB);
+          const bool hand = !dbg_noHand && !all_out;
+          if (hand) mbar_wait_cluster(&bars.pt_empty[pb], ((hi / NPB) & 1) ^ 1);
           FFC_PROF_T(e2);
           FFC_PROF_ADD(prof_e0, e0, e1);
           FFC_PROF_ADD(prof_e1, e1, e2);
@@ -442,7 +483,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           // the chunks.)
           kfloor = max(kfloor, kshared);
           kth = max(kth, kfloor);
-          if (!SV && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+          if (!SV && !all_out && warp_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
           float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
           for (int cc = 0; cc < BN / 32; ++cc) {
@@ -468,31 +509,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             }
             const bool slow = __any_sync(0xffffffffu, excl != 0u);
             uint32_t pk[16];
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              if (dbg_noEpi) {
-                pk[c >> 1] = 0u;
-                continue;
+            // (hard-negative-only items: no softmax term -- ffc.py:86-92 takes the top-k of the raw cosines and nothing else from these
+            // rows -- so no exponentials, no P~ tile, and the O-CTA sits the item out)
+            if (!all_out) {
+  #pragma unroll
+              for (int c = 0; c < 32; c += 2) {
+                if (dbg_noEpi) {
+                  pk[c >> 1] = 0u;
+                  continue;
+                }
+                const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
+                float p0, p1, g0, g1;
+                if (SV) {
+                  const bool m0 = x0 > thr, m1 = x1 > thr;
+                  p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
+                  p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
+                  g0 = m0 ? p0 * SV_T : p0;
+                  g1 = m1 ? p1 * SV_T : p1;
+                } else {
+                  p0 = g0 = ex2f(fmaf(x0, a2, -b2));
+                  p1 = g1 = ex2f(fmaf(x1, a2, -b2));
+                }
+                if (slow) {   // warp-uniform: only chunks that contain an excluded column pay for the per-element test
+                  if ((excl >> c) & 1u) p0 = g0 = 0.f;
+                  if ((excl >> (c + 1)) & 1u) p1 = g1 = 0.f;
+                }
+                l0 += p0;
+                l1 += p1;
+                pk[c >> 1] = pack_bf16(g0, g1);
               }
-              const float x0 = __uint_as_float(v[c]), x1 = __uint_as_float(v[c + 1]);
-              float p0, p1, g0, g1;
-              if (SV) {
-                const bool m0 = x0 > thr, m1 = x1 > thr;
-                p0 = ex2f(fmaf(m0 ? fmaf(SV_T, x0, SV_T - 1.f) : x0, a2, -b2));
-                p1 = ex2f(fmaf(m1 ? fmaf(SV_T, x1, SV_T - 1.f) : x1, a2, -b2));
-                g0 = m0 ? p0 * SV_T : p0;
-                g1 = m1 ? p1 * SV_T : p1;
-              } else {
-                p0 = g0 = ex2f(fmaf(x0, a2, -b2));
-                p1 = g1 = ex2f(fmaf(x1, a2, -b2));
-              }
-              if (slow) {   // warp-uniform: only chunks that contain an excluded column pay for the per-element test
-                if ((excl >> c) & 1u) p0 = g0 = 0.f;
-                if ((excl >> (c + 1)) & 1u) p1 = g1 = 0.f;
-              }
-              l0 += p0;
-              l1 += p1;
-              pk[c >> 1] = pack_bf16(g0, g1);
             }
             // ---- hard-negative top-k on the raw cosines of outlier rows ----
             if (SV) {
@@ -503,11 +548,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
             } else if (warp_out) {
               // Without SV, p~ is monotonic in the cosine: the chunk can only hold a candidate if the maximum of its packed p~ (one
               // bf16x2 max tree; excluded columns are 0) reaches the row's threshold mapped to p~ space.
-              uint32_t m = pk[0];
+              bool mine;
+              if (all_out) {      // no p~ here: the raw cosines' bit patterns (an excluded column can only cause a needless exact scan)
+                int mx = (int)v[0];
 #pragma unroll
-              for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
-              const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
-              unsigned cand = __ballot_sync(0xffffffffu, outl && mf >= pthr);
+                for (int c = 1; c < 32; ++c) mx = max(mx, (int)v[c]);
+                mine = outl && (mx | 31) > kth;      // (| 31: a key carries the column index in the low bits)
+              } else {
+                uint32_t m = pk[0];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) m = max_bf16x2(m, pk[q]);
+                const float mf = fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
+                mine = outl && mf >= pthr;
+              }
+              unsigned cand = __ballot_sync(0xffffffffu, mine);
               if (cand) {
                 FFC_PROF_ADD(prof_trig, 0, 1);
                 if (__popc(cand) > 4) {      // many rows at once (the first tiles of an item): the per-lane scan is cheaper
@@ -543,11 +597,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
                   __syncwarp();
                 }
                 // threshold in p~ space, rounded DOWN to bf16 (the packed values are rounded to nearest): never misses a candidate
-                pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
+                if (!all_out) pthr = __uint_as_float(__float_as_uint(ex2f(fmaf(__int_as_float(kth & (int)TOPK_VAL_MASK), a2, -b2))) & 0xffff0000u);
               }
             }
             // P~[r_local][cc*32 .. +32) = 4 pieces of 16 bytes; each st.async counts itself on the peer's pt_full[pb]
-            if (!dbg_noHand) {
+            if (hand) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 st_async_v4(pt_remote + pt_offset((uint32_t)(cc * 4 + q), (uint32_t)r_local), ptfull_remote, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2],
@@ -569,6 +623,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           FFC_PROF_ADD(prof_e2, e2, e3);
         }
         gi0 += (uint32_t)n_tiles;
+        if (!all_out) hi0 += (uint32_t)n_tiles;
         // ---- per-row partials: combine the three warpgroups through shared memory ----
         // Named barrier 1 (the 12 epilogue warps): every warpgroup has seen its last s_full of the item, i.e. every GEMM-1 that reads
         // this item's P has completed (the next item's P may be stored), and the previous item's staging has been consumed.
@@ -577,7 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         int32_t ti[KMAX];
 #pragma unroll
         for (int q = 0; q < KMAX; ++q) {
-          const bool live = tk[q] > 0;
+          const bool live = tk[q] > 0 && tc[q] >= 0;      // (column -2: a seed from another item's partial -- it is reported there)
           tv[q] = live ? __int_as_float(tk[q] & (int)TOPK_VAL_MASK) : -INFINITY;
           ti[q] = live ? tc[q] + (tk[q] & 31) : -1;
         }
@@ -591,14 +646,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         }
         asm volatile("bar.sync 1, 384;" ::: "memory");
         if (g == 0 && row_ok) {
-          float kthv = -INFINITY;
-#pragma unroll
-          for (int q = 0; q < KMAX; ++q)
-            if (q == k - 1) kthv = tv[q];
 #pragma unroll 1
-          for (int og = 0; og < NEPI - 1; ++og) {
-            lsum += stage_l[og * BM + r_local];
-            if (outl) {
+          for (int og = 0; og < NEPI - 1; ++og) lsum += stage_l[og * BM + r_local];
+          if (outl) {
+            // the own list may have holes where seeds were: rebuild it by insertion, then merge the other warpgroups' lists
+            float ov[KMAX];
+            int32_t oi[KMAX];
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) {
+              ov[q] = tv[q];
+              oi[q] = ti[q];
+              tv[q] = -INFINITY;
+              ti[q] = -1;
+            }
+            float kthv = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) {
+              if (q < k && ov[q] > kthv) {
+                topk_insert<KMAX>(tv, ti, k, ov[q], oi[q]);
+#pragma unroll
+                for (int qq = 0; qq < KMAX; ++qq)
+                  if (qq == k - 1) kthv = tv[qq];
+              }
+            }
+#pragma unroll 1
+            for (int og = 0; og < NEPI - 1; ++og) {
 #pragma unroll 1
               for (int q = 0; q < k; ++q) {
                 const float x = stage_v[(og * BM + r_local) * KMAX + q];
@@ -620,6 +692,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
               sw.topi_part[pr * k + q] = ti[q];
             }
           }
+          __threadfence();      // the partial is visible before the item is flagged finished (below)
+        }
+        if (sidx == 0 && prm.done_flags && g == 0) {
+          asm volatile("bar.sync 4, 128;" ::: "memory");      // warpgroup 0: all 128 rows' partials are out
+          if (warp == 4 && lane == 0) {
+          const int n_row_tiles = (prm.n_rows + BM - 1) / BM;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(prm.done_flags + (int64_t)chunk * n_row_tiles + row0 / BM), "r"(prm.epoch) : "memory");
+          }
         }
       }
       if (warp == 4 && lane == 0) {
@@ -638,7 +718,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       FFC_PROF_DECL(prof_tma);
       for (int ia = pair; ia < n_items; ia += n_pairs) {
         const Item it = decode_item(prm, ia);
-        if (it.n_tiles == 0 || dbg_noO || dbg_noTma) continue;
+        if (it.n_tiles == 0 || it.all_out || dbg_noO || dbg_noTma) continue;
         const CUtensorMap* map_w2 = it.sidx == 0 ? &map_w2a : (it.sidx == 1 ? &map_w2b : &map_w2c);
         for (int t = it.t_begin; t < it.t_begin + it.n_tiles; ++t) {
 #pragma unroll
@@ -677,7 +757,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       for (int ia = pair; ia < n_items; ia += n_pairs) {
         const Item it = decode_item(prm, ia);
         const int n_tiles = it.n_tiles;
-        if (n_tiles == 0) continue;
+        if (n_tiles == 0 || it.all_out) continue;      // (hard-negative-only items have no GEMM-2: the O-CTA sits them out)
         if (ni > 0) {     // the previous item's O has been read out of TMEM by the write-out warps
           FFC_PROF_T(g0);
           mbar_wait(&bars.o_empty, (ni - 1) & 1);
@@ -763,6 +843,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
       for (int ia = pair; ia < n_items; ia += n_pairs) {
         const Item it = decode_item(prm, ia);
         if (dbg_noHand) break;
+        if (it.all_out) continue;
         for (int i = 0; i < it.n_tiles; ++i) {
           if (elect_one()) mbar_expect_tx(&bars.pt_full[pb], PT_BYTES);     // the single arriver of pt_full[pb]
           __syncwarp();
@@ -787,14 +868,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
         const Item it = decode_item(prm, ia);
         const SubSweep& sw = prm.sub[it.sidx];
         const int row0 = it.row0, n_tiles = it.n_tiles;
-        float* dst0 = sw.o_part + ((int64_t)it.chunk * prm.n_rows + row0 + q4 * 32) * D + g * half;
+        if (it.all_out) continue;      // no O partial: the finalize kernels never read the O sums of a hard-negative-only row
+        // destination rows: lane l keeps the probe row of sweep position row0 + q4*32 + l (or -1), handed round by shuffle
+        const int my_pos = row0 + q4 * 32 + lane;
+        const int my_row = my_pos < prm.n_rows ? (prm.row_map ? prm.row_map[my_pos] : my_pos) : -1;
+        float* dst_col = sw.o_part + (int64_t)it.chunk * prm.n_rows * D + g * half;
         if (n_tiles == 0) {
           // an item without columns owes a zero partial (4 rows x 128 B per store instruction)
           for (int c0 = 0; c0 < half; c0 += 32) {
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int r = itr * 4 + (lane >> 3), c = (lane & 7) * 4;
-              if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c) = make_uint4(0u, 0u, 0u, 0u);
+              const int orow = __shfl_sync(0xffffffffu, my_row, r);
+              if (orow >= 0) *reinterpret_cast<uint4*>(dst_col + (int64_t)orow * D + c0 + c) = make_uint4(0u, 0u, 0u, 0u);
             }
           }
           continue;
@@ -820,7 +906,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
           for (int itr = 0; itr < 8; ++itr) {
             const int r = itr * 4 + (lane >> 3), c = lane & 7;
             const uint4 x = *reinterpret_cast<const uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
-            if (row0 + q4 * 32 + r < prm.n_rows) *reinterpret_cast<uint4*>(dst0 + (int64_t)r * D + c0 + c * 4) = x;
+            const int orow = __shfl_sync(0xffffffffu, my_row, r);
+            if (orow >= 0) *reinterpret_cast<uint4*>(dst_col + (int64_t)orow * D + c0 + c * 4) = x;
           }
           __syncwarp();
         }
@@ -865,10 +952,16 @@ struct MapKey {
 struct Sm100Cache {
   PFN_encodeTiled encode = nullptr;
   std::vector<std::pair<MapKey, CUtensorMap>> maps;
+  int32_t* done_flags = nullptr;     // [column chunk][row tile] item-finished flags of the main sweep (value = the launch's epoch)
+  int64_t done_cap = 0;
+  int epoch = 0;
 };
 
 Sm100Cache* sm100_cache_create() { return new Sm100Cache(); }
-void sm100_cache_destroy(Sm100Cache* c) { delete c; }
+void sm100_cache_destroy(Sm100Cache* c) {
+  if (c && c->done_flags) cudaFree(c->done_flags);
+  delete c;
+}
 
 int sm100_get_map(Sm100Cache* c, const void* ptr, int64_t rows, int D, int box_rows, bool chunked3d, CUtensorMap* out) {
   MapKey key{ptr, rows, D, chunked3d ? -box_rows : box_rows};
@@ -1069,6 +1162,8 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
   p.p16 = a.P_bf16;
   p.is_out = a.is_out;
   p.kth_shared = a.kth_shared;
+  p.row_map = a.row_map;
+  p.n_pos_dev = a.row_map ? a.n_pos_dev : nullptr;
   p.a2 = a.scale * LOG2E;
   p.b2 = a.fixed_max * LOG2E;
   p.k = a.k;
@@ -1101,6 +1196,7 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
     sb.thr = w.thr;
     const int64_t n_tiles = std::max<int64_t>(1, ceil_div64(w.n_cols, BN));
     sb.tiles_per_chunk = (int)ceil_div64(n_tiles, w.n_chunks);
+    sb.n_chunks = w.n_chunks;
     sb.item0 = n_items;
     sb.l_part = w.l_part;
     sb.o_part = w.o_part;
@@ -1109,6 +1205,22 @@ int launch_sweeps_sm100(Sm100Cache* cache, const SweepArgs* sweeps, int n_sweeps
     n_items += row_tiles * w.n_chunks;
   }
   p.n_items = n_items;
+  {
+    // item-finished flags of the main sweep (seeds of the hard-negative lists): never reset -- a flag counts only if it holds THIS launch's epoch
+    const int64_t need = (int64_t)sweeps[0].n_chunks * row_tiles;
+    if (need > cache->done_cap) {
+      if (cache->done_flags) FFC_CUDA(cudaFree(cache->done_flags));
+      cache->done_flags = nullptr;
+      cache->done_cap = 0;
+      FFC_CUDA(cudaMalloc(&cache->done_flags, (size_t)need * 2 * sizeof(int32_t)));
+      FFC_CUDA(cudaMemset(cache->done_flags, 0, (size_t)need * 2 * sizeof(int32_t)));
+      cache->done_cap = need * 2;
+    }
+    static const bool no_seed = getenv("FFC_SWEEP_NO_SEED") != nullptr && atoi(getenv("FFC_SWEEP_NO_SEED")) != 0;      // A/B measurements
+    p.done_flags = no_seed ? nullptr : cache->done_flags;
+    p.epoch = ++cache->epoch;
+    if (cache->epoch == 0x7fffffff) cache->epoch = 0;
+  }
 #define FFC_SWEEP_CASE(DV)                                                       \
   case DV:                                                                       \
     return a.sv ? launch_one<true, DV>(maps, p, n_items, s) : launch_one<false, DV>(maps, p, n_items, s);

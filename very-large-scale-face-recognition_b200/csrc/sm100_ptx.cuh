@@ -249,6 +249,7 @@ struct SubSweep {
   const uint32_t* cmask;
   const float* thr;
   int tiles_per_chunk;
+  int n_chunks;       // column chunks of this sweep
   int item0;          // first work item of this sweep (items are [row tile fastest][column chunk])
   float* l_part;
   float* o_part;
@@ -261,6 +262,12 @@ struct Sm100Params {
   const __nv_bfloat16* p16;   // [n_rows, D] probe rows (bf16), loaded straight into TMEM when P_TMEM
   const uint8_t* is_out;
   int32_t* kth_shared;        // [n_rows] shared hard-negative threshold (integer key), zeroed by the prep kernel
+  // CTA-pair kernel: sweep position -> probe row, positives first and hard-negative-only ("outlier") rows last, and the number of
+  // positives (device side).  Items whose rows are all at or beyond it run GEMM-1 and the top-k only.  NULL: identity, no such items.
+  const int32_t* row_map;
+  const int32_t* n_pos_dev;
+  int32_t* done_flags;        // CTA-pair kernel, main sweep: [column chunk][row tile] == epoch once that item's top-k partial is in global memory
+  int epoch;                  // (a later item of the same rows seeds its hard-negative lists from the finished items' partials)
   float a2, b2;       // p~ = 2^(a2 * z - b2)
   int k;
   int debug;   // bottleneck isolation BITMASK, only in FFC_SM100_DEBUG_BUILD builds; results are WRONG when any bit is set:
