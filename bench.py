@@ -64,7 +64,8 @@ def config_of(w, world):
     """The `config` object of the JSON line: the same for our arm and the reference arm."""
     return dict(workload=w['name'], rows_per_pass_per_gpu=w['B'], passes_per_step=2, identities=w['N'], queue=w['Q'], feat_dim=w['D'],
                 loss=w['loss_type'], margin=w['margin'], scale=w['scale'], sharding=('none' if world == 1 else f'queue columns /{world}'),
-                l2_policy='working set (bf16 queue %.0f MB per rank) exceeds the 126 MB L2' % (w['Q'] // world * w['D'] * 2 / 1e6))
+                l2_policy='working set (bf16 queue %.0f MB per rank) exceeds the 126 MB L2' % (w['Q'] // world * w['D'] * 2 / 1e6),
+                labels='pinned host int64 tensors (the reference passes CPU LongTensors, main.py:59-60); embeddings resident in HBM')
 
 
 def make_batches(w, n_batches, seed, rank=0, world=1):
@@ -385,8 +386,10 @@ def run_ours(args, w):
     # exactly 1, the reference's Arc NaN hazard
     n_b = args.steps + args.warmup
     host = make_batches(w, n_b, seed=1234, rank=rank, world=world)
-    # sharded head: labels stay on the host (pinned), as in the reference's loop; one GPU: device-resident
-    devb = [(x.to(dev), y.to(dev), xl.pin_memory() if world > 1 else xl.to(dev), yl.pin_memory() if world > 1 else yl.to(dev)) for x, y, xl, yl in host]
+    # embeddings device-resident; labels stay on the host (pinned), as in the reference's loop (main.py:59-60: CPU LongTensors) -- at
+    # every N, so that the per-N values are comparable: host labels let the LRU bookkeeping of a step run ahead on the bookkeeping
+    # stream (one GPU) / be handed over by prefetch() (sharded head), under the previous step's sweeps
+    devb = [(x.to(dev), y.to(dev), xl.pin_memory(), yl.pin_memory()) for x, y, xl, yl in host]
 
     def barrier():
         if world > 1:

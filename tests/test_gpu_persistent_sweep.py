@@ -2,8 +2,10 @@
 the item list -- barrier phases, TMEM and the pipeline rings run on across items, the O write-out is staged through the P~ buffer of the
 item's last tile.  The parity suites normally run one pair per item (their shapes have few items); here they are re-run in a subprocess
 with the grid forced down to one or two pairs (FFC_SWEEP_PAIRS, read once per process), so that every launch walks several items per
-pair: main / side items, items without columns, ragged row and column tiles, several column chunks.  And one shape that is persistent by
-itself (18 row tiles x 8 chunks + 36 side items) against the fp64 check mode."""
+pair: main / side items, items without columns, ragged row and column tiles, several column chunks.  FFC_SWEEP_ROWMAP=1 additionally
+forces the "hard-negative-only rows last" row order (normally used only by launches several waves deep), so that the fixtures with unknown
+probe labels run row tiles without exponentials / GEMM-2 and seed their top-k lists from finished items.  And one many-row-tile shape
+against the fp64 check mode."""
 import os
 import subprocess
 import sys
@@ -17,7 +19,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('env', [dict(FFC_SWEEP_PAIRS='1'), dict(FFC_SWEEP_PAIRS='2', FFC_SWEEP_CHUNKS='3')], ids=['one_pair', 'two_pairs_three_chunks'])
+@pytest.mark.parametrize('env', [dict(FFC_SWEEP_PAIRS='1'), dict(FFC_SWEEP_PAIRS='2', FFC_SWEEP_CHUNKS='3', FFC_SWEEP_ROWMAP='1'), dict(FFC_SWEEP_ROWMAP='1')],
+                         ids=['one_pair', 'two_pairs_three_chunks_rowmap', 'rowmap'])
 def test_parity_suites_on_a_forced_persistent_grid(env):
     # (tests/test_gpu_fast_paths.py is left out: it compares sharded against unsharded runs to 2e-5, which presumes both use the same
     # column-chunk split; the overrides change the split, i.e. the fp32 summation order)

@@ -91,7 +91,7 @@ def test_drop_in_for_the_reference_module_with_its_own_backbones(net_type, D, B,
     if net_type == 'mobile':
         # On this image (torch 2.11 + its cuDNN, B200) the reference's MobileFaceNet -- alone, without any code of this repo --
         # returns NaN from its second forward on once a backward has produced non-finite gradients, which fp16 autocast with a
-        # GradScaler-sized factor does on the first steps (tools/debug_mobile4.py: reference FFC / bare backbone, cuDNN on -> NaN,
+        # GradScaler-sized factor does on the first steps (tools/reference_mobilefacenet_nan_probe.py: reference FFC / bare backbone, cuDNN on -> NaN,
         # cuDNN off -> finite).  The backbones are outside the hot path; the comparison runs them on the native kernels.
         ctx = torch.backends.cudnn.flags(enabled=False)
     else:

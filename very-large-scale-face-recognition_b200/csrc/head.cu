@@ -1321,11 +1321,19 @@ __global__ void __launch_bounds__(128) head_thr_from_tgt_kernel(const float* __r
   thr[n + i] = has ? tgt[n + i] - margin : INFINITY;
 }
 
-// The merged bf16 AM / Arc sweep (CTA-pair kernel) takes its rows in "hard-negative-only rows last" order; FFC_SWEEP_NO_ROWMAP=1 keeps the
-// identity order (A/B measurements).  SV sweeps and the check mode do not use it.
-static bool use_row_map(const ffc_head* h) {
+// The merged bf16 AM / Arc sweep takes its rows in "hard-negative-only rows last" order when the launch is several waves of work items
+// deep (the 4- / 8-way shard shapes): row tiles made of such rows then cost about half a tile (no exponentials, no GEMM-2) and the
+// hardware deals the items out as pairs free up.  In a one-wave launch (C2, C4 on one GPU) the kernel ends with its slowest item, and
+// concentrating the hard-negative scans in a few items makes that one slower (C2: +11 %), so the identity order stays.
+// FFC_SWEEP_NO_ROWMAP=1: never (A/B measurements); FFC_SWEEP_ROWMAP=1: at any shape (tests).  SV sweeps and the check mode do not use it.
+static bool use_row_map(const ffc_head* h, int n_rows) {
   static const bool off = getenv("FFC_SWEEP_NO_ROWMAP") != nullptr && atoi(getenv("FFC_SWEEP_NO_ROWMAP")) != 0;
-  return !off && h->cfg.precision == FFC_PREC_BF16 && h->cfg.loss_type != FFC_LOSS_SV;
+  static const bool force = getenv("FFC_SWEEP_ROWMAP") != nullptr && atoi(getenv("FFC_SWEEP_ROWMAP")) != 0;      // tests: at any shape
+  if (off || h->cfg.precision != FFC_PREC_BF16 || h->cfg.loss_type == FFC_LOSS_SV) return false;
+  if (force) return true;
+  const int row_tiles = (n_rows + 127) / 128;
+  const int chunks = sm100_pick_chunks(n_rows, h->cfg.q_local, h->cfg.feat_dim, (int)std::min<int64_t>(h->part_rows_cap / std::max(1, n_rows) - 2, h->max_chunks));
+  return (int64_t)row_tiles * chunks > 2 * 74;
 }
 
 // phase: 1 = prep only, 2 = sweeps only (prep was run by ffc_head_prep; SV thresholds are re-derived from out->tgt), 3 = both
@@ -1353,7 +1361,7 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
     if (bf16)
       head_prep_fused_kernel<true><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
                                                         in->n_ones, c.max_rows, nullptr, h->side_bf16, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
-                                                        out->tgt, sv ? h->thr : nullptr, use_row_map(h) ? h->row_map : nullptr, h->part_ctr);
+                                                        out->tgt, sv ? h->thr : nullptr, use_row_map(h, n) ? h->row_map : nullptr, h->part_ctr);
     else
       head_prep_fused_kernel<false><<<grid, 128, 0, s>>>(in->p_f32, h->p16, in->label, n, c.col_offset, c.q_local, D, qf, qh, in->cmask, in->ones_list,
                                                          in->n_ones, c.max_rows, h->side_f32, nullptr, h->tcol, h->tpos, h->is_out, h->kth_shared, cur, nxt, c.margin,
@@ -1379,7 +1387,7 @@ static int head_sweep_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_hea
   a.D = D;
   a.is_out = h->is_out;
   a.kth_shared = h->kth_shared;
-  if (use_row_map(h)) {      // (written by this pass's prep launch)
+  if (use_row_map(h, n)) {      // (written by this pass's prep launch)
     a.row_map = h->row_map;
     a.n_pos_dev = h->part_ctr + 1;
   }
