@@ -417,8 +417,9 @@ class FFC(FFCHead):
 
     def __init__(self, net_type, feat_dim, queue_size=7409, scale=32.0, loss_type='AM', margin=0.4, momentum=0.99,
                  neg_margin=0.25, pretrained_model_path=None, num_class=None, *, precision='bf16', max_batch=1024,
-                 probe_net=None, gallery_net=None, device=None):
-        FFCHead.__init__(self, feat_dim, queue_size, scale, loss_type, margin, precision=precision, max_batch=max_batch, device=device)
+                 probe_net=None, gallery_net=None, device=None, queue_grad=False):
+        FFCHead.__init__(self, feat_dim, queue_size, scale, loss_type, margin, precision=precision, max_batch=max_batch, device=device,
+                         queue_grad=queue_grad)
         self.probe_net = probe_net if probe_net is not None else create_net(net_type, feat_dim=feat_dim, fp16=True)
         self.gallery_net = gallery_net if gallery_net is not None else create_net(net_type, feat_dim=feat_dim, fp16=True)
         self.neg_margin = neg_margin          # stored, unused (as in the reference, ffc.py:44)
