@@ -328,6 +328,20 @@ def kernel_micro(head, w, dev, world):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def l2_to_sm_note(rows, q_local, D, sweep_ms):
+    """What bounds the D = 512 sweep (profiles/r2_sweep_ncu_summary.md): every 128-column tile of W (128 x D bf16) is streamed
+    from L2 into BOTH CTAs of its pair, once per 128-row tile of probe rows.  The byte count is the kernel's tiling, the rate follows from
+    the measured launch time; ncu's l1tex__m_xbar2l1tex_read_bytes of the C3 launch is 19.38 GB: the 17.18 GB counted here + 2.15 GB of
+    p~ tiles handed from the S-CTA to the O-CTA over DSMEM (32 KB per tile, delivered through the same crossbar) + P tiles and side sweeps."""
+    if D != 512 or sweep_ms <= 0:
+        return None
+    row_tiles, col_tiles = (rows + 127) // 128, (q_local + 127) // 128
+    w_bytes = 2.0 * row_tiles * col_tiles * 128 * D * 2
+    return dict(what='L2 -> SM delivery of the queue tiles (both CTAs of a pair stream every tile), not the tensor pipe',
+                w_tile_bytes_per_launch=w_bytes, delivered_tb_per_s=w_bytes / (sweep_ms * 1e-3) / 1e12,
+                evidence='profiles/r2_sweep_ncu_summary.md, profiles/r2_persistent_sweep.md')
+
+
 def softmax_rows(head, rows):
     """Rows of the last pass that have a softmax term (label known), rounded up to whole 128-row tiles: the rows GEMM-2 runs for."""
     lab = None
@@ -507,7 +521,8 @@ def run_ours(args, w):
                                   kernel='ffc_head_sweep_sm100_kernel (main sweep)', launches=int(sweep_n), avg_ms=sweep_ms / max(1, sweep_n),
                                   algorithmic_flops_per_launch=flops, rows_per_launch=rows_per_sweep, rows_with_softmax_term=soft_rows,
                                   peak_kind=('bf16_tflops_sustained' if long_run else 'bf16_tflops (burst)') + f' ({pk["src"]}; timed region {ms / 1e3:.2f} s)',
-                                  frac_of_burst=ach / pk['burst'], frac_of_sustained=ach / pk['sustained'], sweep_share_of_step=sweep_ms / ms),
+                                  frac_of_burst=ach / pk['burst'], frac_of_sustained=ach / pk['sustained'], sweep_share_of_step=sweep_ms / ms,
+                                  limiter=l2_to_sm_note(rows_per_sweep, q_local, D, sweep_ms / max(1, sweep_n))),
                     clocks=clk, loss=loss_val)
         if cb is not None:
             line['cpu_baseline'] = cb
