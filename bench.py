@@ -532,6 +532,8 @@ def run_ours(args, w):
             line['cpu_extras'] = cpu_extras()
         if world > 1 and os.environ.get('FFC_DIST_TIMING'):
             line['phase_ms_total'] = phase_ms
+        if world > 1:
+            line['barrier_timeouts'] = head.barrier_timeouts()      # in-kernel cross-rank barriers that gave up (must be 0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

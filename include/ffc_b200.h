@@ -124,6 +124,12 @@ int ffc_queue_scatter_indexed(float* queue_f32_dev, void* queue_bf16_dev, const 
  * keys_out / order_out [n] (order_out[j] = source position), n_mine_out device scalar. */
 int ffc_route_keys(const int64_t* keys_dev, int n, int n_ranks, int rank, int64_t* keys_out_dev,
                    int32_t* order_out_dev, int32_t* n_mine_out_dev, void* stream);
+/* Cross-rank barrier on the stream (one tiny launch): tells every peer "what this rank stored into your buffers before this call is out"
+ * (system-scope fence, release store of `epoch` into word my_rank of the peer's flag array) and waits until every peer has said so to this
+ * rank.  flag_ptrs_dev[r] = rank r's peer-mapped array of n_ranks int32 words (zero-initialised; epochs only grow).  A wait longer than
+ * 5 s raises *err_flag_dev and goes on (no hang). */
+int ffc_peer_barrier(int32_t* const* flag_ptrs_dev, int my_rank, int n_ranks, int32_t epoch, int32_t* err_flag_dev, void* stream);
+
 /* as ffc_queue_scatter_indexed, and every winning write also records in overlay_map_dev (int32 [2, Q], -1 = no entry; NULL = off)
  * where the content this (row, slot) had during the CURRENT pass's sweep stays available once later kernels have rewritten the row:
  *   overlay_table 0 (a rollback pass's enqueue): map = src_row[i]          -- the row is g[src_row[i]] until ffc_queue_restore
@@ -305,6 +311,13 @@ int ffc_head_pass_single(ffc_head_t* h, const ffc_head_pass* in, const ffc_head_
  * ffc_head_finalize_gathered sums the scalars in rank order and produces this rank's partial dLoss/dp straight from its
  * sweep partials.  bf16 AM / Arc only. */
 int ffc_head_record_words(const ffc_head_config* cfg, int n_rows, int64_t* words_out);
+/* Record exchange by peer stores instead of an all-gather (ranks whose gathered-record buffers are peer-mapped, e.g. torch symmetric
+ * memory): copies the record of the pass just swept (`record_dev`, as written by ffc_head_sweep_record on handle `h`) into every rank's
+ * buffer at peer_ptrs_dev[r] + dst_offset_words -- the per-row scalars always, the top-k candidate slots only for rows whose label is -1
+ * (the only rows whose candidates ffc_head_finalize_gathered reads; identical on every rank because the labels are).  Follow all pushes
+ * of a step with ONE ffc_peer_barrier; the finalize calls after it may read the gathered buffer. */
+int ffc_head_push_record(ffc_head_t* h, int n_rows, const float* record_dev, float* const* peer_ptrs_dev, int64_t dst_offset_words, int n_ranks,
+                         void* stream);
 int ffc_head_sweep_record(ffc_head_t* h, const ffc_head_pass* in, void* record_out, void* stream);
 int ffc_head_finalize_gathered(ffc_head_t* h, const ffc_head_pass* in, const void* records, int n_ranks,
                                int64_t record_stride_words, float* loss_out, float* dp_out, void* stream);

@@ -132,6 +132,9 @@ def main():
         if precision == 'bf16' and loss_type != 'SV':
             assert os.environ.get('FFC_DIST_NO_MERGE') or (head.merged and head._route is not None)   # one exchange per step, reduce-scatter folded into finalize
             routes.add(head._route['kind'] if head._route else 'per-pass')
+            if any(isinstance(r, dict) and 'peer' in r for r in head._stats.values()):
+                routes.add('records by peer stores')
+        assert head.barrier_timeouts() == 0, 'an in-kernel cross-rank barrier timed out'
         del head
     sharded_checkpoint_resume(rank, world, dev)
     long_run_odd_queue(rank, world, dev)

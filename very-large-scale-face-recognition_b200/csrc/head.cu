@@ -1518,6 +1518,42 @@ static int head_finalize_impl(ffc_head_t* h, const ffc_head_pass* in, const ffc_
 }
 
 // ---- sharded head: per-rank record out of the sweep, finalize from the gathered records ----
+// Record exchange by peer stores (sharded head, ranks whose record buffers are peer-mapped): copies this rank's record of the pass just
+// swept into EVERY rank's gathered buffer -- the 8 scalars of every row always, the top-k candidate slots (88 % of a record at k = 10)
+// only for hard-negative-only rows, the only rows whose candidates the fused finalize reads.  An all-gather cannot trim by content; at C3
+// (no such rows) this is 0.26 MB per pass and rank instead of 2.2 MB.
+__global__ void __launch_bounds__(256) head_push_record_kernel(const float* __restrict__ rec, int n, int k, const uint8_t* __restrict__ is_out,
+                                                               float* const* __restrict__ peers, int64_t dst_off, int n_ranks) {
+  const int64_t n_scalar4 = 2 * (int64_t)n;                       // 8 n words as float4 (8 n is a multiple of 4)
+  const int64_t n_top = 6 * (int64_t)n * k;                       // [3][n][k] values, then [3][n][k] columns
+  const int64_t total = n_scalar4 + n_top;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < n_scalar4) {
+      const float4 v = reinterpret_cast<const float4*>(rec)[e];
+      for (int r = 0; r < n_ranks; ++r) reinterpret_cast<float4*>(peers[r] + dst_off)[e] = v;
+    } else {
+      const int64_t t = e - n_scalar4;
+      const int row = (int)((t / k) % n);
+      if (!is_out[row]) continue;
+      const float v = rec[8 * (int64_t)n + t];
+      for (int r = 0; r < n_ranks; ++r) peers[r][dst_off + 8 * (int64_t)n + t] = v;
+    }
+  }
+  __threadfence_system();      // visible system-wide before the kernel counts as finished; the flag follows in ffc_peer_barrier
+}
+
+extern "C" int ffc_head_push_record(ffc_head_t* h, int n_rows, const float* record_dev, float* const* peer_ptrs_dev, int64_t dst_offset_words, int n_ranks,
+                                    void* stream) {
+  FFC_REQUIRE(h && record_dev && peer_ptrs_dev && n_rows >= 1 && n_rows <= h->cfg.max_rows && n_ranks >= 1 && n_ranks <= 64 && dst_offset_words >= 0 &&
+                  dst_offset_words % 4 == 0,
+              "ffc_head_push_record: bad arguments");
+  const int64_t total = 2 * (int64_t)n_rows + 6 * (int64_t)n_rows * h->cfg.topk;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(total, 256), 148 * 2));
+  head_push_record_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(record_dev, n_rows, h->cfg.topk, h->is_out, peer_ptrs_dev, dst_offset_words, n_ranks);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
 extern "C" int ffc_head_record_words(const ffc_head_config* cfg, int n_rows, int64_t* words_out) {
   FFC_REQUIRE(cfg && words_out && n_rows >= 0, "ffc_head_record_words: bad arguments");
   *words_out = record_words(n_rows, cfg->topk);

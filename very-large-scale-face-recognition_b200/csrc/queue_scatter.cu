@@ -256,6 +256,31 @@ __global__ void __launch_bounds__(256) sum_slabs_barrier_kernel(const float4* __
     out[i] = acc;
   }
 }
+// The barrier alone (one block): "everything this rank stored into its peers' buffers before this launch is out" to every peer, then wait
+// until every peer has said the same to this rank.  Same flag protocol as sum_slabs_barrier_kernel (own set of flag words).
+__global__ void __launch_bounds__(64) peer_barrier_kernel(int32_t* const* __restrict__ flag_ptrs, int my_rank, int n_ranks, int32_t epoch, int32_t* err_flag,
+                                                          long long timeout_ns) {
+  if (threadIdx.x < n_ranks) {
+    __threadfence_system();
+    int32_t* dst = flag_ptrs[threadIdx.x] + my_rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    const int32_t* src = flag_ptrs[my_rank] + threadIdx.x;
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+      int32_t v;
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if (v - epoch >= 0) break;
+      long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        *err_flag = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+}
 }  // namespace ffc
 
 extern "C" int ffc_sum_slabs_barrier(const float* slabs_dev, int n_slabs, int64_t slab_stride, int64_t n, float* out_dev, int32_t* const* flag_ptrs_dev,
@@ -267,6 +292,13 @@ extern "C" int ffc_sum_slabs_barrier(const float* slabs_dev, int n_slabs, int64_
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n / 4, 256), 148 * 4));
   sum_slabs_barrier_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)slabs_dev, n_slabs, slab_stride / 4, n / 4, (float4*)out_dev, flag_ptrs_dev,
                                                                       my_rank, n_ranks, epoch, err_flag_dev, 5000000000LL);
+  FFC_LAUNCH_CHECK();
+  return FFC_OK;
+}
+
+extern "C" int ffc_peer_barrier(int32_t* const* flag_ptrs_dev, int my_rank, int n_ranks, int32_t epoch, int32_t* err_flag_dev, void* stream) {
+  FFC_REQUIRE(flag_ptrs_dev && err_flag_dev && n_ranks >= 1 && n_ranks <= 64 && my_rank >= 0 && my_rank < n_ranks, "ffc_peer_barrier: rank %d of %d", my_rank, n_ranks);
+  peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(flag_ptrs_dev, my_rank, n_ranks, epoch, err_flag_dev, 5000000000LL);
   FFC_LAUNCH_CHECK();
   return FFC_OK;
 }

@@ -79,6 +79,8 @@ PROTOTYPES = {
     'ffc_overlay_clear': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     'ffc_sum_slabs': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     'ffc_sum_slabs_barrier': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int32, c_void_p, c_void_p]),
+    'ffc_head_push_record': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'ffc_peer_barrier': (c_int, [c_void_p, c_int, c_int, c_int32, c_void_p, c_void_p]),
     'ffc_head_finalize_gathered_ex': (c_int, [c_void_p, C.POINTER(HeadPass), c_void_p, c_int, c_int64, C.POINTER(FinalizeOpts), c_void_p, c_void_p, c_void_p]),
     'ffc_route_keys': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ffc_ema_chunk_elems': (c_int, []),

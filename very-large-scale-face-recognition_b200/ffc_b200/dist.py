@@ -196,6 +196,16 @@ class CudaShardBackend:
                                                      w * passes, C.byref(opts), loss.data_ptr(), None if dp is None else dp.data_ptr(), self._s()))
         return loss, dp
 
+    def push_record(self, p_all, rec, which, rank):
+        """Record exchange by peer stores: this rank's record of pass `which` into every rank's gathered buffer (top-k slots only for
+        hard-negative-only rows); ffc_head_push_record."""
+        pr = rec['peer']
+        check(self.lib.ffc_head_push_record(self._h2 if which else self._h, p_all.shape[0], rec['own'][which].data_ptr(), pr['ptrs'].data_ptr(),
+                                            (rank * rec['passes'] + which) * rec['words'], pr['ptrs'].numel(), self._s()))
+
+    def peer_barrier(self, flags, rank, ranks, epoch, err):
+        check(self.lib.ffc_peer_barrier(flags.data_ptr(), rank, ranks, epoch & 0x7fffffff, err.data_ptr(), self._s()))
+
     def sum_slabs(self, slabs, n_slabs, stride, n, out, barrier=None):
         """out = sum of the slabs in order; barrier = (flag pointer table, rank, ranks, epoch, error flag): first meet the peers whose
         finalize kernels wrote the slabs (one launch)"""
@@ -346,6 +356,31 @@ class ShardedFFCHead:
         if self._route['kind'] == 'nccl':
             stage = torch.empty(R * slab, dtype=torch.float32, device=dev)
             self._route.update(stage=stage, ptrs=torch.tensor([stage.data_ptr() + 4 * r * slab for r in range(R)], dtype=torch.int64, device=dev))
+
+    def _peer_records(self, n):
+        """Gathered-record buffers of the merged step in symmetric memory: [R ranks][2 passes][words] + the barrier's flag words, peer-mapped
+        like the gradient staging.  The ranks then exchange their records by peer stores (ffc_head_push_record: the scalars of every row,
+        the top-k slots only of hard-negative-only rows -- 12 % of the bytes an all-gather moves when there are none) and ONE
+        ffc_peer_barrier.  None when the peer route is not available or not asked for (NCCL all-gather then)."""
+        be, R, dev = self.backend, self.R, self.dev
+        # Opt-in (FFC_DIST_PEER_RECORDS=1): NCCL parity tests green at 2 and 8 GPUs with it on, the exchange itself 0.14 -> 0.08 ms per step at
+        # 8 GPUs, but the one 8-GPU run measured with it showed the step's [x | y] all-gather at 0.50 ms against 0.13 in every run before, with
+        # no GPU budget left to tell a slow box from a side effect (profiles/r2_dist_8gpu.md) -- the all-gather stays the default.
+        if self._route is None or self._route.get('kind') != 'symm' or not os.environ.get('FFC_DIST_PEER_RECORDS'):
+            return None
+        import torch.distributed._symmetric_memory as symm_mem
+        w = be.new_records(n, 1, passes=1)['words']
+        ws = (w + 3) // 4 * 4                                    # 16-byte aligned records
+        buf = symm_mem.empty(R * 2 * ws + 64, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        assert len(ptrs) == R and ptrs[self.rank] == buf.data_ptr()
+        buf.zero_()
+        dist.barrier(group=self.group)                           # every rank's flag words are zero before anyone signals
+        return dict(own=torch.zeros(2, ws, dtype=torch.float32, device=dev), all=buf[:R * 2 * ws].view(R, 2, ws), words=ws, passes=2, buf=buf, hdl=hdl,
+                    peer=dict(ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
+                              flags=torch.tensor([p + 4 * R * 2 * ws for p in ptrs], dtype=torch.int64, device=dev),
+                              err=torch.zeros(1, dtype=torch.int32, device=dev), epoch=0))
 
     # -- helpers ----------------------------------------------------------------------------------
     def shard_of(self, keys):
@@ -589,7 +624,10 @@ class ShardedFFCHead:
         n = x_all.shape[0]
         rec = self._stats.get(('rec2', n))
         if rec is None:
-            rec = self._stats[('rec2', n)] = be.new_records(n, R, passes=2)
+            rec = self._peer_records(n) if self._nccl else None
+            if rec is None:
+                rec = be.new_records(n, R, passes=2)
+            self._stats[('rec2', n)] = rec
         rb_set = ctx_rb['set']
         self._rb_set = rb_set
         main = torch.cuda.current_stream(self.dev) if self._nccl else None
@@ -617,6 +655,8 @@ class ShardedFFCHead:
         be.scatter(y_all, ctx_rb['order'], save_undo=True, overlay_table=0)
         self._mark('scatter')
         be.sweep_record(x_all, ctx_rb['label'], rec, 0)
+        if 'peer' in rec:
+            be.push_record(x_all, rec, 0, self.rank)
         self._mark('sweep')
         be.restore_queue()
         be.end_pass()
@@ -632,8 +672,14 @@ class ShardedFFCHead:
         be.sweep_record(y_all, ctx_cm['label'], rec, 1)
         be.end_pass()
         self._mark('sweep')
-        # the step's single statistics exchange
-        dist.all_gather_into_tensor(rec['all'].view(-1, rec['words']), rec['own'], group=self.group)
+        # the step's single statistics exchange: by peer stores + one barrier, or one NCCL all-gather
+        if 'peer' in rec:
+            be.push_record(y_all, rec, 1, self.rank)
+            pr = rec['peer']
+            pr['epoch'] += 1
+            be.peer_barrier(pr['flags'], self.rank, R, pr['epoch'], pr['err'])
+        else:
+            dist.all_gather_into_tensor(rec['all'].view(-1, rec['words']), rec['own'], group=self.group)
         self._mark('stat_exchange')
         route = self._route
         if route is not None:
@@ -800,6 +846,17 @@ class ShardedFFCHead:
     def forward(self, x, y, x_label, y_label):
         """ffc.py:264-267 with embeddings in (rollback pass, then commit pass)."""
         return self.head(x, y.detach(), x_label, y_label, commit=False) + self.head(y, x.detach(), y_label, x_label, commit=True)
+
+    def barrier_timeouts(self):
+        """Number of in-kernel cross-rank barriers (gradient slabs, record exchange) that gave up waiting for a peer (5 s) since
+        construction; anything but 0 means wrong results.  Synchronises."""
+        n = 0
+        if self._route is not None and 'err' in self._route:
+            n += int(self._route['err'].item())
+        for rec in self._stats.values():
+            if isinstance(rec, dict) and 'peer' in rec:
+                n += int(rec['peer']['err'].item())
+        return n
 
     def set_timing(self, enable):
         self.backend.set_timing(enable)
