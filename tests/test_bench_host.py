@@ -65,3 +65,27 @@ def test_reference_arm_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=120, env=dict(env, RANK='1', WORLD_SIZE='2'))
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_executed_flop_accounting_and_limiter_note():
+    """roofline.achieved counts executed tensor FLOPs: every row's cosines, and the gradient sum only for the row tiles that hold a row with a
+    softmax term (hard-negative-only rows are swept last and skip GEMM-2); the limiter note counts the W tiles both CTAs of a pair stream."""
+    b = _bench()
+
+    class OneGpu:          # FFCHead: bookkeeping set 1 = the commit pass
+        def __init__(self, lab):
+            self._sets = [dict(label=None), dict(label=lab)]
+
+    class Sharded:         # ShardedFFCHead: the commit pass's all-reduced labels
+        def __init__(self, lab):
+            self._last = dict(label=lab)
+
+    lab = torch.full((512,), -1, dtype=torch.int32)
+    lab[:130] = 7                                     # 130 rows with a known label -> two row tiles run GEMM-2
+    assert b.softmax_rows(OneGpu(lab), 512) == 256 and b.softmax_rows(Sharded(lab), 512) == 256
+    assert b.softmax_rows(OneGpu(torch.zeros(1024, dtype=torch.int32)), 1024) == 1024       # C3: every label known -> 4*B*Q*D
+    assert b.softmax_rows(OneGpu(torch.full((300,), -1, dtype=torch.int32)), 300) == 0
+    assert b.softmax_rows(object(), 77) == 77         # unknown head type: assume every row
+    note = b.l2_to_sm_note(1024, 1 << 20, 512, 1.443)
+    assert note['w_tile_bytes_per_launch'] == 2 * 8 * 8192 * 128 * 512 * 2 and 11.5 < note['delivered_tb_per_s'] < 12.5
+    assert b.l2_to_sm_note(1024, 1 << 20, 128, 0.45) is None          # the one-CTA kernel loads every tile once: no such note

@@ -275,6 +275,7 @@ def _worker_merged(rank, world, port, loss_type, ret):
         t = torch.tensor([naive_wrong, head.backend.overlay_reads, head.prefetch_hits])
         dist.all_reduce(t)
         assert int(t[0]) > 0 and int(t[1]) > 0 and int(t[2]) == world * (steps // 2), t.tolist()       # the overlay was needed, and it was read
+        assert head.barrier_timeouts() == 0            # (no in-kernel barriers on the CPU stand-in: the counter exists and reads 0)
         ret[rank] = 'ok'
     finally:
         dist.destroy_process_group()
